@@ -1,0 +1,404 @@
+// bvh_build.cuh — the per-element steps of the GPU BVH build (replaces hiprtBuildGeometry,
+// common/loader.hpp:68-112).  bvh_build.cu launches one thread per element for each step:
+//
+//   1 tri_bounds      triangle AABB + scene bounds (atomic min/max)
+//   2 morton_key      63-bit Morton code of the centroid            -> radix sort (cub)
+//   3 lbvh_node       Karras 2012 binary radix tree, one inner node per thread
+//   4 lbvh_refit      bottom-up boxes and triangle counts, second arrival at a node continues
+//   5 collapse_item   top-down, level by level: open the largest-area child until a node has 8 children,
+//                     subtrees of <= 3 triangles become leaf children; children are matched to octant
+//                     slots, boxes are quantised outward to the node's 8-bit grid, triangles are written
+//                     as 48-byte records next to each other
+//
+// The functions are host-callable too, so tests/emu can run the identical build sequentially on the
+// CPU; the library itself only ever runs them on the device.
+#pragma once
+#include "bvh.cuh"
+
+namespace crt
+{
+#if defined(__CUDA_ARCH__)
+#define CRT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define CRT_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define CRT_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define CRT_FENCE() __threadfence()
+#else
+template <class T>
+inline T crt_host_fetch_add(T* p, T v)
+{
+    const T old = *p;
+    *p = old + v;
+    return old;
+}
+#define CRT_ATOMIC_ADD(p, v) crt_host_fetch_add((p), (v))
+#define CRT_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
+#define CRT_ATOMIC_MAX(p, v) (*(p) > (v) ? *(p) : (*(p) = (v)))
+#define CRT_FENCE()
+#endif
+
+// order-preserving float <-> uint mapping for atomic min/max on floats
+CRT_HD uint32_t float_to_ordered(float f)
+{
+    const uint32_t u = f2u(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+CRT_HD float ordered_to_float(uint32_t u) { return u2f((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+struct BuildTri  // the nine vertex floats of a reference Triangle (60-byte stride, 4-byte aligned)
+{
+    f3 v0, v1, v2;
+};
+CRT_HD BuildTri load_build_tri(const float* tris60, uint32_t i)
+{
+    const float* p = tris60 + (size_t)i * 15;
+    return {{p[0], p[1], p[2]}, {p[3], p[4], p[5]}, {p[6], p[7], p[8]}};
+}
+
+struct Aabb
+{
+    f3 lo, hi;
+};
+CRT_HD float fmin3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+CRT_HD float fmax3(float a, float b, float c) { return fmaxf(a, fmaxf(b, c)); }
+CRT_HD Aabb tri_aabb(const BuildTri& t)
+{
+    return {{fmin3(t.v0.x, t.v1.x, t.v2.x), fmin3(t.v0.y, t.v1.y, t.v2.y), fmin3(t.v0.z, t.v1.z, t.v2.z)},
+            {fmax3(t.v0.x, t.v1.x, t.v2.x), fmax3(t.v0.y, t.v1.y, t.v2.y), fmax3(t.v0.z, t.v1.z, t.v2.z)}};
+}
+CRT_HD Aabb aabb_union(const Aabb& a, const Aabb& b)
+{
+    return {{fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z)},
+            {fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z)}};
+}
+CRT_HD float aabb_half_area(const Aabb& b)
+{
+    const float x = b.hi.x - b.lo.x, y = b.hi.y - b.lo.y, z = b.hi.z - b.lo.z;
+    return x * y + y * z + z * x;
+}
+
+// ---- step 1: scene bounds; bounds6 = ordered-uint {lo.xyz, hi.xyz}
+CRT_HD void tri_bounds(uint32_t i, const float* tris60, uint32_t* bounds6)
+{
+    const Aabb b = tri_aabb(load_build_tri(tris60, i));
+    CRT_ATOMIC_MIN(bounds6 + 0, float_to_ordered(b.lo.x));
+    CRT_ATOMIC_MIN(bounds6 + 1, float_to_ordered(b.lo.y));
+    CRT_ATOMIC_MIN(bounds6 + 2, float_to_ordered(b.lo.z));
+    CRT_ATOMIC_MAX(bounds6 + 3, float_to_ordered(b.hi.x));
+    CRT_ATOMIC_MAX(bounds6 + 4, float_to_ordered(b.hi.y));
+    CRT_ATOMIC_MAX(bounds6 + 5, float_to_ordered(b.hi.z));
+}
+
+// ---- step 2: 63-bit Morton key (21 bits per axis) of the box centre
+CRT_HD uint64_t spread21(uint64_t x)
+{
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+CRT_HD uint64_t morton_key(uint32_t i, const float* tris60, f3 scene_lo, f3 scene_inv_extent)
+{
+    const Aabb b = tri_aabb(load_build_tri(tris60, i));
+    const float cx = ((b.lo.x + b.hi.x) * 0.5f - scene_lo.x) * scene_inv_extent.x;
+    const float cy = ((b.lo.y + b.hi.y) * 0.5f - scene_lo.y) * scene_inv_extent.y;
+    const float cz = ((b.lo.z + b.hi.z) * 0.5f - scene_lo.z) * scene_inv_extent.z;
+    const float s = 2097151.0f;  // 2^21 - 1
+    const uint64_t qx = (uint64_t)fminf(fmaxf(cx * s, 0.0f), s);
+    const uint64_t qy = (uint64_t)fminf(fmaxf(cy * s, 0.0f), s);
+    const uint64_t qz = (uint64_t)fminf(fmaxf(cz * s, 0.0f), s);
+    return (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+}
+
+// ---- step 3: binary radix tree.  Node ids: inner i in [0, n-2]; leaf j is (n-1) + j.
+struct BinTree
+{
+    uint32_t n;         // triangles (= leaves)
+    uint32_t* left;     // [n-1]
+    uint32_t* right;    // [n-1]
+    uint32_t* parent;   // [2n-1]
+    uint32_t* first;    // [n-1]  first sorted position covered by inner node
+    uint32_t* count;    // [n-1]  triangles under inner node
+    float* box;         // [2n-1][6]  padded AABB
+    uint32_t* visits;   // [n-1]  refit arrival counters (zeroed)
+};
+
+CRT_HD int lbvh_delta(const uint64_t* keys, uint32_t n, int i, int j)
+{
+    if (j < 0 || j >= (int)n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + clz32((uint32_t)i ^ (uint32_t)j);  // duplicate keys: fall back to the position
+    return clz64(a ^ b);
+}
+
+CRT_HD void lbvh_node(uint32_t idx, const uint64_t* keys, const BinTree& bt)
+{
+    const uint32_t n = bt.n;
+    const int i = (int)idx;
+    const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2)
+    {
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    const int gamma = i + s * d + (d < 0 ? -1 : 0);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const uint32_t l_id = (lo == gamma) ? (n - 1) + (uint32_t)gamma : (uint32_t)gamma;
+    const uint32_t r_id = (hi == gamma + 1) ? (n - 1) + (uint32_t)(gamma + 1) : (uint32_t)(gamma + 1);
+    bt.left[idx] = l_id;
+    bt.right[idx] = r_id;
+    bt.parent[l_id] = idx;
+    bt.parent[r_id] = idx;
+    bt.first[idx] = (uint32_t)lo;
+    bt.count[idx] = (uint32_t)(hi - lo + 1);
+    if (idx == 0) bt.parent[0] = 0xffffffffu;
+}
+
+// ---- step 4: bottom-up boxes.  One thread per leaf; `pad` is added on every side of every leaf box.
+CRT_HD void store_box(float* box, uint32_t id, const Aabb& b)
+{
+    float* p = box + (size_t)id * 6;
+    p[0] = b.lo.x; p[1] = b.lo.y; p[2] = b.lo.z;
+    p[3] = b.hi.x; p[4] = b.hi.y; p[5] = b.hi.z;
+}
+CRT_HD Aabb load_box(const float* box, uint32_t id)
+{
+    const float* p = box + (size_t)id * 6;
+    return {{p[0], p[1], p[2]}, {p[3], p[4], p[5]}};
+}
+CRT_HD void lbvh_refit(uint32_t leaf, const float* tris60, const uint32_t* sorted_idx, float pad, const BinTree& bt)
+{
+    Aabb b = tri_aabb(load_build_tri(tris60, sorted_idx[leaf]));
+    b.lo = b.lo - f3{pad, pad, pad};
+    b.hi = b.hi + f3{pad, pad, pad};
+    uint32_t id = (bt.n - 1) + leaf;
+    store_box(bt.box, id, b);
+    if (bt.n == 1) return;
+    uint32_t p = bt.parent[id];
+    while (p != 0xffffffffu)
+    {
+        CRT_FENCE();
+        if (CRT_ATOMIC_ADD(bt.visits + p, 1u) == 0u) return;  // first arrival: the sibling will finish
+        CRT_FENCE();
+#if defined(__CUDA_ARCH__)
+        // the sibling's box was written by another thread: read it through L2
+        const volatile float* vb = bt.box;
+        const uint32_t l = bt.left[p], r = bt.right[p];
+        Aabb lb, rb;
+        lb.lo = {vb[(size_t)l * 6 + 0], vb[(size_t)l * 6 + 1], vb[(size_t)l * 6 + 2]};
+        lb.hi = {vb[(size_t)l * 6 + 3], vb[(size_t)l * 6 + 4], vb[(size_t)l * 6 + 5]};
+        rb.lo = {vb[(size_t)r * 6 + 0], vb[(size_t)r * 6 + 1], vb[(size_t)r * 6 + 2]};
+        rb.hi = {vb[(size_t)r * 6 + 3], vb[(size_t)r * 6 + 4], vb[(size_t)r * 6 + 5]};
+        b = aabb_union(lb, rb);
+#else
+        b = aabb_union(load_box(bt.box, bt.left[p]), load_box(bt.box, bt.right[p]));
+#endif
+        store_box(bt.box, p, b);
+        p = bt.parent[p];
+    }
+}
+
+// ---- step 5: collapse to the wide tree
+struct CollapseItem
+{
+    uint32_t bnode;  // binary node to expand
+    uint32_t wnode;  // wide node to write
+};
+struct WideOut
+{
+    WideNode* nodes;
+    WideTri* tris;
+    uint32_t* node_count;   // allocator, starts at 1 (root)
+    uint32_t* tri_count;    // allocator, starts at 0
+    CollapseItem* next;     // next level's work
+    uint32_t* next_count;
+};
+
+CRT_HD uint32_t bin_tri_count(const BinTree& bt, uint32_t id) { return id >= bt.n - 1 ? 1u : bt.count[id]; }
+CRT_HD uint32_t bin_first(const BinTree& bt, uint32_t id) { return id >= bt.n - 1 ? id - (bt.n - 1) : bt.first[id]; }
+
+CRT_HD uint8_t quant_exponent(float extent)
+{
+    // smallest e with extent / 2^e <= 255, as a biased exponent; extent >= 0
+    if (!(extent > 0.0f)) return 1;
+    int e = (int)((f2u(extent) >> 23) & 0xffu) - 127 - 7;  // 2^e ~ extent / 128 .. extent / 256
+    if (e < -126) e = -126;
+    while (extent / u2f((uint32_t)(e + 127) << 23) > 255.0f) ++e;
+    return (uint8_t)(e + 127);
+}
+
+CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint32_t* sorted_idx, const BinTree& bt,
+                          const WideOut& out)
+{
+    uint32_t ch[8];
+    int cnt;
+    if (bin_tri_count(bt, it.bnode) <= (uint32_t)kLeafMaxTris)
+    {
+        ch[0] = it.bnode;  // whole tree is one leaf (n <= 3)
+        cnt = 1;
+    }
+    else
+    {
+        ch[0] = bt.left[it.bnode];
+        ch[1] = bt.right[it.bnode];
+        cnt = 2;
+        while (cnt < 8)
+        {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int k = 0; k < cnt; k++)
+            {
+                if (bin_tri_count(bt, ch[k]) <= (uint32_t)kLeafMaxTris) continue;
+                const float a = aabb_half_area(load_box(bt.box, ch[k]));
+                if (a > best_area)
+                {
+                    best_area = a;
+                    best = k;
+                }
+            }
+            if (best < 0) break;
+            const uint32_t c = ch[best];
+            ch[best] = bt.left[c];
+            ch[cnt++] = bt.right[c];
+        }
+    }
+
+    // node box = union of the (already padded) child boxes
+    Aabb cb[8];
+    Aabb nb = load_box(bt.box, ch[0]);
+    cb[0] = nb;
+    for (int k = 1; k < cnt; k++)
+    {
+        cb[k] = load_box(bt.box, ch[k]);
+        nb = aabb_union(nb, cb[k]);
+    }
+
+    // octant slots: slot bit a set = child lies on the + side of axis a.  Greedy maximum of
+    // sum_a (+-)(centre_child - centre_node)_a over the free (child, slot) pairs.
+    int slot_of[8];
+    {
+        const f3 nc = (nb.lo + nb.hi) * 0.5f;
+        float cost[8][8];
+        for (int k = 0; k < cnt; k++)
+        {
+            const f3 d = (cb[k].lo + cb[k].hi) * 0.5f - nc;
+            for (int s = 0; s < 8; s++)
+                cost[k][s] = ((s & 1) ? d.x : -d.x) + ((s & 2) ? d.y : -d.y) + ((s & 4) ? d.z : -d.z);
+        }
+        uint32_t child_free = (1u << cnt) - 1u, slot_free = 0xffu;
+        for (int round = 0; round < cnt; round++)
+        {
+            int bk = -1, bs = -1;
+            float bc = -3.0e38f;
+            for (int k = 0; k < cnt; k++)
+            {
+                if (!((child_free >> k) & 1u)) continue;
+                for (int s = 0; s < 8; s++)
+                    if (((slot_free >> s) & 1u) && cost[k][s] > bc)
+                    {
+                        bc = cost[k][s];
+                        bk = k;
+                        bs = s;
+                    }
+            }
+            slot_of[bk] = bs;
+            child_free &= ~(1u << bk);
+            slot_free &= ~(1u << bs);
+        }
+    }
+    int child_in_slot[8];
+    for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
+    for (int k = 0; k < cnt; k++) child_in_slot[slot_of[k]] = k;
+
+    WideNode wn;
+    wn.px = nb.lo.x;
+    wn.py = nb.lo.y;
+    wn.pz = nb.lo.z;
+    wn.ex = quant_exponent(nb.hi.x - nb.lo.x);
+    wn.ey = quant_exponent(nb.hi.y - nb.lo.y);
+    wn.ez = quant_exponent(nb.hi.z - nb.lo.z);
+    const float inv_cell[3] = {1.0f / u2f((uint32_t)wn.ex << 23), 1.0f / u2f((uint32_t)wn.ey << 23),
+                               1.0f / u2f((uint32_t)wn.ez << 23)};
+
+    uint32_t n_inner = 0, n_leaf_tris = 0;
+    uint8_t imask = 0;
+    for (int s = 0; s < 8; s++)
+    {
+        const int k = child_in_slot[s];
+        if (k < 0) continue;
+        const uint32_t tc = bin_tri_count(bt, ch[k]);
+        if (tc > (uint32_t)kLeafMaxTris)
+        {
+            imask |= (uint8_t)(1u << s);
+            n_inner++;
+        }
+        else n_leaf_tris += tc;
+    }
+    const uint32_t child_base = n_inner ? CRT_ATOMIC_ADD(out.node_count, n_inner) : 0u;
+    const uint32_t tri_base = n_leaf_tris ? CRT_ATOMIC_ADD(out.tri_count, n_leaf_tris) : 0u;
+    const uint32_t next_base = n_inner ? CRT_ATOMIC_ADD(out.next_count, n_inner) : 0u;
+    wn.imask = imask;
+    wn.child_base = child_base;
+    wn.tri_base = tri_base;
+
+    uint32_t inner_rank = 0, tri_off = 0;
+    const float nlo[3] = {nb.lo.x, nb.lo.y, nb.lo.z};
+    for (int s = 0; s < 8; s++)
+    {
+        const int k = child_in_slot[s];
+        if (k < 0)
+        {
+            wn.meta[s] = 0;
+            for (int a = 0; a < 3; a++)
+            {
+                wn.qlo[a][s] = 255;
+                wn.qhi[a][s] = 0;
+            }
+            continue;
+        }
+        const float clo[3] = {cb[k].lo.x, cb[k].lo.y, cb[k].lo.z}, chi[3] = {cb[k].hi.x, cb[k].hi.y, cb[k].hi.z};
+        for (int a = 0; a < 3; a++)
+        {
+            const float ql = floorf((clo[a] - nlo[a]) * inv_cell[a]);
+            const float qh = ceilf((chi[a] - nlo[a]) * inv_cell[a]);
+            wn.qlo[a][s] = (uint8_t)fminf(fmaxf(ql, 0.0f), 255.0f);
+            wn.qhi[a][s] = (uint8_t)fminf(fmaxf(qh, 0.0f), 255.0f);
+        }
+        const uint32_t tc = bin_tri_count(bt, ch[k]);
+        if (tc > (uint32_t)kLeafMaxTris)
+        {
+            wn.meta[s] = 0xff;
+            out.next[next_base + inner_rank] = CollapseItem{ch[k], child_base + inner_rank};
+            inner_rank++;
+        }
+        else
+        {
+            wn.meta[s] = (uint8_t)((tc << 5) | tri_off);
+            const uint32_t f = bin_first(bt, ch[k]);
+            for (uint32_t j = 0; j < tc; j++)
+            {
+                const uint32_t prim = sorted_idx[f + j];
+                const BuildTri t = load_build_tri(tris60, prim);
+                WideTri wt;
+                wt.v0x = t.v0.x; wt.v0y = t.v0.y; wt.v0z = t.v0.z; wt.prim = (int32_t)prim;
+                wt.v1x = t.v1.x; wt.v1y = t.v1.y; wt.v1z = t.v1.z; wt.pad1 = 0.0f;
+                wt.v2x = t.v2.x; wt.v2y = t.v2.y; wt.v2z = t.v2.z; wt.pad2 = 0.0f;
+                out.tris[tri_base + tri_off + j] = wt;
+            }
+            tri_off += tc;
+        }
+    }
+    out.nodes[it.wnode] = wn;
+}
+}  // namespace crt

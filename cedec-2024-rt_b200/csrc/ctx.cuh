@@ -1,0 +1,74 @@
+// ctx.cuh — context object, error plumbing and launch helpers behind the C ABI (include/cedecrt.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/cedecrt.h"
+#include "bvh.cuh"
+
+struct crt_ctx
+{
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the stream every launch and copy goes to
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    int math_mode = CRT_MATH_LIBDEVICE;
+    int sm_count = 0;
+    char name[256] = {0};
+    unsigned long long launches = 0;  // kernels launched through this context (bench.py: gpu_launches)
+};
+
+struct crt_geometry_t
+{
+    crt::WideNode* nodes = nullptr;
+    crt::WideTri* tris = nullptr;
+    const crt_triangle* src = nullptr;  // the triangle array the tree was built over
+    size_t n_tris = 0, n_nodes = 0;
+    int max_depth = 0;
+    float build_ms = 0.0f;
+    float pad = 0.0f;
+    int device = 0;
+    crt::Bvh view() const { return crt::Bvh{nodes, tris}; }
+};
+
+namespace crt
+{
+void set_error(const char* fmt, ...);
+
+#define CRT_CUDA(call)                                                                        \
+    do                                                                                        \
+    {                                                                                         \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+        {                                                                                     \
+            crt::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return e__ == cudaErrorMemoryAllocation ? CRT_ENOMEM : CRT_ECUDA;                 \
+        }                                                                                     \
+    } while (0)
+
+#define CRT_REQUIRE(cond, msg)                          \
+    do                                                  \
+    {                                                   \
+        if (!(cond))                                    \
+        {                                               \
+            crt::set_error("%s: %s", __func__, (msg));  \
+            return CRT_EINVAL;                          \
+        }                                               \
+    } while (0)
+
+inline int check_launch(crt_ctx* ctx, const char* what)
+{
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+    {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return CRT_ECUDA;
+    }
+    return CRT_OK;
+}
+
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+}  // namespace crt

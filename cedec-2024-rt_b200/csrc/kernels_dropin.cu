@@ -1,0 +1,289 @@
+// kernels_dropin.cu — the reference's kernel entry points on the reference's own AoS buffers
+// ("drop-in mode"): same parameter lists as the KERNELs of examples/10_restir_di/10_restir_di.cu,
+// common/kernels/common.cu, 06_ao_hiprt.cu, 07_pt.cu, 08_nee.cu and 09_ris.cu, so the unmodified host
+// loop (10_restir_di.cpp:229-380) can drive them through crt_launch / the crt_* exports.
+//
+// Thread mapping: one thread per pixel like the reference, but a 256-thread block covers a 32x8 pixel
+// tile and each warp an 8x4 sub-tile (the reference's linear tid gives 32x1 strips): primary rays of a
+// warp stay coherent and the Gaussian neighbourhoods of a block overlap in L1.  Randomness is keyed on
+// (xi, yi, frame, stage), so the mapping does not change any result.
+#include "ctx.cuh"
+#include "restir_pixel.cuh"
+
+namespace crt
+{
+constexpr int kTileW = 32, kTileH = 8;
+
+// pixel of this thread
+struct TilePix
+{
+    Pix px;
+    bool in;
+};
+__device__ __forceinline__ TilePix this_pixel(int W, int H)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xi = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
+    const int yi = blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
+    return {make_pix(xi, yi, W, H), xi < W && yi < H};
+}
+static dim3 tile_grid(int W, int H) { return dim3((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH); }
+
+__global__ void __launch_bounds__(256) k_raycast(int W, int H, Bvh bvh, crt_raygen raygen, crt_visibility* vis)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in) px_raycast(t.px, W, H, bvh, raygen, vis);
+}
+__global__ void __launch_bounds__(256)
+    k_generate_candidate(int W, int H, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+                         const uint32_t* lights, uint32_t n_lights, crt_options options, crt_reservoir* out)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in) px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, n_lights, make_opt(options), AosStore{out});
+}
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    k_temporal(int W, int H, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+               crt_options options, const crt_reservoir* prev, crt_reservoir* cur)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in)
+        px_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, make_opt(options),
+                                AosStore{const_cast<crt_reservoir*>(prev)}, AosStore{cur});
+}
+// 10_restir_di.cu:239-254 (the first buffer is the source).  Every pixel is copied, so the bottom-up
+// index permutation does not matter: plain word copy.
+__global__ void __launch_bounds__(256) k_save_temporal(size_t n_words, const uint32_t* src, uint32_t* dst)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    k_spatial(int W, int H, int frame, int pass, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+              crt_options options, const crt_reservoir* in, crt_reservoir* out)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in)
+        px_spatial<Math<MODE>>(t.px, W, H, frame, pass, bvh, tris60, vis, eye, make_opt(options),
+                               AosStore{const_cast<crt_reservoir*>(in)}, AosStore{out});
+}
+__global__ void __launch_bounds__(256)
+    k_resolve(crt_float4* accum, int W, int H, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+              crt_options options, const crt_reservoir* res)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in) px_resolve(t.px, accum, bvh, tris60, vis, eye, make_opt(options), AosStore{const_cast<crt_reservoir*>(res)});
+}
+
+// ---- common/kernels/common.cu:4-17 and :30-74 (every pixel is touched: plain linear sweeps)
+__global__ void __launch_bounds__(256) k_clear(size_t n, float4* buf)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        buf[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_tone_mapping(size_t n, uint32_t* pixels, const float4* accum)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const float4 a = accum[i];
+        pixels[i] = tone_map_rgba8<Math<MODE>>(f4{a.x, a.y, a.z, a.w});
+    }
+}
+template <int EX, int MODE>
+__global__ void __launch_bounds__(256)
+    k_path_trace(int W, int H, int frame, Bvh bvh, const float* tris60, const uint32_t* lights, uint32_t n_lights,
+                 crt_raygen raygen, crt_options options, crt_float4* accum)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in)
+        px_path_trace<EX, Math<MODE>>(t.px, W, H, frame, bvh, tris60, lights, n_lights, raygen, make_opt(options), accum);
+}
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    k_ao(uint32_t* pixels, crt_raygen raygen, int W, int H, Bvh bvh, const float* tris60, int n_rays)
+{
+    const TilePix t = this_pixel(W, H);
+    if (t.in) pixels[t.px.idx] = px_ao<Math<MODE>>(t.px, raygen, W, H, bvh, tris60, n_rays);
+}
+}  // namespace crt
+
+// ======================================================================================= C ABI
+using namespace crt;
+
+namespace
+{
+inline size_t bsize(const crt_buffer& b) { return (size_t)CRT_BUFFER_SIZE(b); }
+inline f3 to_f3(const crt_float3& v) { return f3{v.x, v.y, v.z}; }
+inline unsigned sweep_blocks(crt_ctx* ctx, size_t n)
+{
+    const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+}  // namespace
+
+#define CRT_CHECK_IMAGE(W, H) CRT_REQUIRE((W) > 0 && (H) > 0 && (size_t)(W) * (size_t)(H) < 0x7fffffffull, "bad image size")
+#define CRT_CHECK_BUF(b, n, what) CRT_REQUIRE((b).data != nullptr && bsize(b) >= (size_t)(n), what " buffer too small or null")
+
+extern "C" int crt_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_raygen raygen,
+                           crt_buffer visibility_buffer)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
+    (void)triangles;  // the reference's raycast does not read it either (10_restir_di.cu:9-34)
+    k_raycast<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, geom->view(), raygen,
+                                                       (crt_visibility*)visibility_buffer.data);
+    return check_launch(ctx, "raycast");
+}
+
+extern "C" int crt_generate_candidate(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                      crt_buffer visibility_buffer, crt_float3 eye, crt_buffer lights,
+                                      crt_options options, crt_buffer reservoirs)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
+    CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    CRT_REQUIRE(bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
+    CRT_REQUIRE(bsize(lights) < 0xffffffffull, "too many lights");
+    k_generate_candidate<<<tile_grid(W, H), 256, 0, ctx->stream>>>(
+        W, H, frame, geom->view(), (const float*)triangles.data, (const crt_visibility*)visibility_buffer.data,
+        to_f3(eye), (const uint32_t*)lights.data, (uint32_t)bsize(lights), options, (crt_reservoir*)reservoirs.data);
+    return check_launch(ctx, "generate_candidate");
+}
+
+extern "C" int crt_temporal_resampling(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                       crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                                       crt_buffer previous_reservoirs, crt_buffer reservoirs)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
+    CRT_CHECK_BUF(previous_reservoirs, (size_t)W * H, "previous reservoir");
+    CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_temporal<1> : k_temporal<0>;
+    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, frame, geom->view(), (const float*)triangles.data,
+                                               (const crt_visibility*)visibility_buffer.data, to_f3(eye), options,
+                                               (const crt_reservoir*)previous_reservoirs.data,
+                                               (crt_reservoir*)reservoirs.data);
+    return check_launch(ctx, "temporal_resampling");
+}
+
+extern "C" int crt_save_temporal_reservoir(crt_ctx* ctx, int W, int H, crt_buffer src, crt_buffer dst)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(src, (size_t)W * H, "source reservoir");
+    CRT_CHECK_BUF(dst, (size_t)W * H, "destination reservoir");
+    const size_t n_words = (size_t)W * H * (sizeof(crt_reservoir) / 4);
+    k_save_temporal<<<sweep_blocks(ctx, n_words), 256, 0, ctx->stream>>>(n_words, (const uint32_t*)src.data,
+                                                                        (uint32_t*)dst.data);
+    return check_launch(ctx, "save_temporal_reservoir");
+}
+
+extern "C" int crt_spatial_resampling(crt_ctx* ctx, int W, int H, int frame, int pass, crt_geometry geom,
+                                      crt_buffer triangles, crt_buffer visibility_buffer, crt_float3 eye,
+                                      crt_options options, crt_buffer previous_reservoirs, crt_buffer reservoirs)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
+    CRT_CHECK_BUF(previous_reservoirs, (size_t)W * H, "input reservoir");
+    CRT_CHECK_BUF(reservoirs, (size_t)W * H, "output reservoir");
+    CRT_REQUIRE(previous_reservoirs.data != reservoirs.data, "spatial_resampling cannot run in place");
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_spatial<1> : k_spatial<0>;
+    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, frame, pass, geom->view(), (const float*)triangles.data,
+                                               (const crt_visibility*)visibility_buffer.data, to_f3(eye), options,
+                                               (const crt_reservoir*)previous_reservoirs.data,
+                                               (crt_reservoir*)reservoirs.data);
+    return check_launch(ctx, "spatial_resampling");
+}
+
+extern "C" int crt_resolve(crt_ctx* ctx, crt_buffer accumulation, int W, int H, crt_geometry geom,
+                           crt_buffer triangles, crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                           crt_buffer reservoirs)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(accumulation, (size_t)W * H, "accumulation");
+    CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
+    CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    k_resolve<<<tile_grid(W, H), 256, 0, ctx->stream>>>((crt_float4*)accumulation.data, W, H, geom->view(),
+                                                       (const float*)triangles.data,
+                                                       (const crt_visibility*)visibility_buffer.data, to_f3(eye),
+                                                       options, (const crt_reservoir*)reservoirs.data);
+    return check_launch(ctx, "resolve");
+}
+
+extern "C" int crt_clear(crt_ctx* ctx, crt_buffer buffer, int W, int H)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(buffer, (size_t)W * H, "accumulation");
+    const size_t n = (size_t)W * H;
+    k_clear<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (float4*)buffer.data);
+    return check_launch(ctx, "clear");
+}
+
+extern "C" int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accumulation, int W, int H)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(pixels, (size_t)W * H * 4, "pixel");
+    CRT_CHECK_BUF(accumulation, (size_t)W * H, "accumulation");
+    const size_t n = (size_t)W * H;
+    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_tone_mapping<1> : k_tone_mapping<0>;
+    k<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (uint32_t*)pixels.data, (const float4*)accumulation.data);
+    return check_launch(ctx, "tone_mapping");
+}
+
+template <int EX>
+static int path_trace(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                      crt_buffer lights, crt_raygen raygen, crt_options options, crt_buffer accumulation)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(accumulation, (size_t)W * H, "accumulation");
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    CRT_REQUIRE(EX == 7 || bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
+    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_path_trace<EX, 1> : k_path_trace<EX, 0>;
+    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, frame, geom->view(), (const float*)triangles.data,
+                                               (const uint32_t*)lights.data, (uint32_t)bsize(lights), raygen, options,
+                                               (crt_float4*)accumulation.data);
+    return check_launch(ctx, "path_trace");
+}
+extern "C" int crt_path_trace_07(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                 crt_raygen raygen, crt_options options, crt_buffer accumulation)
+{
+    return path_trace<7>(ctx, W, H, frame, geom, triangles, crt_buffer{nullptr, 0}, raygen, options, accumulation);
+}
+extern "C" int crt_path_trace_08(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                 crt_buffer lights, crt_raygen raygen, crt_options options, crt_buffer accumulation)
+{
+    return path_trace<8>(ctx, W, H, frame, geom, triangles, lights, raygen, options, accumulation);
+}
+extern "C" int crt_path_trace_09(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                 crt_buffer lights, crt_raygen raygen, crt_options options, crt_buffer accumulation)
+{
+    return path_trace<9>(ctx, W, H, frame, geom, triangles, lights, raygen, options, accumulation);
+}
+
+extern "C" int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int W, int H, crt_geometry geom,
+                         crt_buffer triangles, int n_rays)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    CRT_CHECK_BUF(pixels, (size_t)W * H * 4, "pixel");
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    CRT_REQUIRE(n_rays > 0, "n_rays must be positive");
+    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_ao<1> : k_ao<0>;
+    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>((uint32_t*)pixels.data, raygen, W, H, geom->view(),
+                                               (const float*)triangles.data, n_rays);
+    return check_launch(ctx, "ao_06");
+}

@@ -1,0 +1,310 @@
+// restir_core.cuh — per-pixel logic of the ReSTIR DI path (examples 06-10), layout-agnostic.
+// The kernels (kernels_*.cu) decide how reservoirs are stored (reference AoS or SoA planes) and hand
+// register-resident values to these functions.  Every function cites the reference lines it implements;
+// arithmetic order follows the reference exactly (see vecmath.cuh for the numerics contract).
+#pragma once
+#include "bvh.cuh"
+
+namespace crt
+{
+#if defined(__CUDA_ARCH__)
+#define CRT_LDG(p) __ldg(p)
+#else
+#define CRT_LDG(p) (*(p))
+#endif
+
+// ---- reference Triangle (common/core.hpp:38-43): 15 floats, 60-byte stride, 4-byte aligned
+struct TriRef
+{
+    const float* p;
+    CRT_HD f3 v(int k) const { return {CRT_LDG(p + 3 * k), CRT_LDG(p + 3 * k + 1), CRT_LDG(p + 3 * k + 2)}; }
+    CRT_HD f3 color() const { return {CRT_LDG(p + 9), CRT_LDG(p + 10), CRT_LDG(p + 11)}; }
+    CRT_HD f3 emissive() const { return {CRT_LDG(p + 12), CRT_LDG(p + 13), CRT_LDG(p + 14)}; }
+};
+CRT_HD TriRef tri_at(const float* tris60, int index) { return TriRef{tris60 + (size_t)index * 15}; }
+CRT_HD bool has_emission(f3 e) { return e.x > 0.0f || e.y > 0.0f || e.z > 0.0f; }  // core.hpp:65-69
+CRT_HD f3 tri_normal(f3 v0, f3 v1, f3 v2) { return normalize(cross(v1 - v0, v2 - v0)); }      // core.hpp:50-55
+CRT_HD float tri_area(f3 v0, f3 v1, f3 v2) { return 0.5f * length(cross(v1 - v0, v2 - v0)); }  // core.hpp:57-62
+CRT_HD f3 bary_point(f3 v0, f3 v1, f3 v2, float u, float v) { return (1.0f - u - v) * v0 + u * v1 + v * v2; }
+
+// ---- camera (common/camera.hpp:27-35); pixel -> (u,v) = (xi/W, yi/H) as in 10_restir_di.cu:24
+struct RayGen
+{
+    f3 origin, right, up;
+};
+CRT_HD void shoot(const RayGen& rg, float u, float v, f3& ro, f3& rd)
+{
+    const f3 forward = normalize(cross(rg.up, rg.right));
+    const f3 to = rg.origin + forward + mix(-rg.right, rg.right, u) + mix(rg.up, -rg.up, v);
+    ro = rg.origin;
+    rd = normalize(to - rg.origin);
+}
+
+// ---- raytrace.hpp:45-52 — origin p0 + 1e-3 n0 (core.hpp:32-36), direction p1 - p0 (not renormalised),
+// t in [0, 0.99]; the reference asks for the closest hit but only uses hit / no hit -> any-hit walk.
+CRT_HD float check_visibility(const Bvh& bvh, f3 p0, f3 n0, f3 p1)
+{
+    Hit h;
+    return trace<true>(bvh, p0 + 0.001f * n0, p1 - p0, 0.0f, 0.99f, h) ? 0.0f : 1.0f;
+}
+
+// ---- surfaces (core.hpp:188-207 and 152-165)
+struct Surf
+{
+    f3 p, n;
+};
+CRT_HD Surf surface_from_visibility(const TriRef& t, float u, float v, f3 eye)
+{
+    const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2);
+    Surf s{bary_point(v0, v1, v2, u, v), tri_normal(v0, v1, v2)};
+    const f3 view = normalize(eye - s.p);
+    if (dot(view, s.n) < 0.0f) s.n = -s.n;
+    return s;
+}
+CRT_HD Surf surface_from_hit(const TriRef& t, f3 ro, f3 rd, float thit)
+{
+    Surf s{ro + thit * rd, tri_normal(t.v(0), t.v(1), t.v(2))};
+    if (dot(-rd, s.n) < 0.0f) s.n = -s.n;
+    return s;
+}
+
+// ---- sampling (core.hpp:76-89, 237-295)
+template <class M>
+CRT_HD f3 sample_hemisphere(float r0, float r1, float r2)
+{
+    const float theta = r0 * 2.0f * kPi;
+    float radius = r1 + r2;
+    if (1.0f < radius) radius = 2.0f - radius;
+    const float x = M::cos(theta) * radius;
+    const float z = M::sin(theta) * radius;
+    const float yy = 1.0f - radius * radius;
+    return {x, sqrtf(yy < 0.0f ? 0.0f : yy), z};
+}
+CRT_HD f2 warp_unit_triangle(float x, float y)  // Heitz 2019, core.hpp:237-252
+{
+    if (y > x) { x *= 0.5f; y -= x; }
+    else { y *= 0.5f; x -= y; }
+    return {x, y};
+}
+struct LightSample
+{
+    f3 p, n, emissive;
+    float area;
+};
+// core.hpp:261-285 plus what the callers read from the same triangle (emissive, area_of)
+CRT_HD LightSample sample_light(const float* tris60, const uint32_t* lights, uint32_t n_lights, float rv0, float rv1,
+                                float rv2)
+{
+    uint32_t nth = (uint32_t)(rv0 * (float)n_lights);
+    if (nth == n_lights) nth = n_lights - 1;
+    const TriRef t = tri_at(tris60, (int)CRT_LDG(lights + nth));
+    const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2);
+    const f2 b = warp_unit_triangle(rv1, rv2);
+    LightSample ls;
+    ls.p = bary_point(v0, v1, v2, b.x, b.y);
+    const f3 c = cross(v1 - v0, v2 - v0);
+    const float len = length(c);
+    ls.n = c / len;            // normal_of
+    ls.area = 0.5f * len;      // area_of
+    ls.emissive = t.emissive();
+    return ls;
+}
+CRT_HD float geometry_term(f3 p0, f3 n0, f3 p1, f3 n1)  // core.hpp:287-295
+{
+    f3 v = p1 - p0;
+    const float sqr = dot(v, v);
+    v = normalize(v);
+    return fabsf(dot(v, n0)) * fabsf(dot(-v, n1)) / sqr;
+}
+
+// ---- reservoir (common/reservoir.hpp)
+struct Sample
+{
+    f3 op, on, hp, hn, rad;  // origin position/normal, hit position/normal, radiance
+    uint32_t vis;            // bool visibility
+};
+struct Res
+{
+    Sample s;
+    float w_sum, ucw;
+    int M;
+};
+CRT_HD Res empty_res()
+{
+    Res r;
+    r.s.op = r.s.on = r.s.hp = r.s.hn = r.s.rad = f3{0.0f, 0.0f, 0.0f};
+    r.s.vis = 0;
+    r.w_sum = r.ucw = 0.0f;
+    r.M = 0;
+    return r;
+}
+CRT_HD float target_function(const Bvh& bvh, f3 p0, f3 n0, f3 p1, f3 n1, f3 radiance, bool shadowed)  // :42-59
+{
+    const float G = geometry_term(p0, n0, p1, n1);
+    if (shadowed) return kInvPi * G * check_visibility(bvh, p0, n0, p1) * luminance(radiance);
+    return kInvPi * G * luminance(radiance);
+}
+template <class M>
+CRT_HD float rejection_heuristics(const Sample& s0, const Sample& s1, f3 eye)  // reservoir.hpp:61-87
+{
+    const float d0 = length(s0.op - eye);
+    const float d1 = length(s1.op - eye);
+    const float diff = (d1 - d0) * (d1 - d0) / d0;
+    float w = 1.0f;
+    w *= M::exp(-32.0f * diff);
+    const float c = dot(s0.on, s1.on);
+    w *= M::pow(c > 0.0f ? c : 0.0f, 8.0f);
+    return w;
+}
+template <class M>
+CRT_HD f2 sample_2d_gaussian(float rv0, float rv1)  // reservoir.hpp:89-95
+{
+    const float a = -2.0f * M::log(rv0);
+    const float radius = sqrtf(a > 0.0f ? a : 0.0f);
+    const float phi = 2.0f * kPi * rv1;
+    return {radius * M::cos(phi), radius * M::sin(phi)};
+}
+CRT_HD float ucw_of(const Res& r, float p_hat) { return p_hat > 0.0f ? r.w_sum / ((float)r.M * p_hat) : 0.0f; }
+
+struct Opt  // the fields of common/options.hpp:4-23 the kernels read
+{
+    bool accumulate, temporal, spatial, shadowed, reuse;
+    int max_depth, ris_count, spatial_count;
+    float radius;
+    f3 sky;
+};
+CRT_HD Opt make_opt(const crt_options& o)
+{
+    Opt r;
+    r.accumulate = o.accumulate != 0;
+    r.temporal = o.use_temporal_resampling != 0;
+    r.spatial = o.use_spatial_resampling != 0;
+    r.shadowed = o.use_shadowed_target_function != 0;
+    r.reuse = o.use_visibility_reuse != 0;
+    r.max_depth = o.max_depth;
+    r.ris_count = o.ris_sample_count;
+    r.spatial_count = o.spatial_resampling_sample_count;
+    r.radius = o.spatial_resampling_radius;
+    r.sky = f3{o.sky_color.x, o.sky_color.y, o.sky_color.z};
+    return r;
+}
+
+// RIS over the emissive triangles: generate_candidate (10_restir_di.cu:78-111) and 09_ris.cu:66-100.
+// Randoms are drawn left to right: light pick, two barycentric randoms, then the reservoir's u.
+CRT_HD Res ris_candidates(const Bvh& bvh, const float* tris60, const Surf& surf, const uint32_t* lights,
+                          uint32_t n_lights, int count, bool shadowed, Pcg& rng)
+{
+    Res r = empty_res();
+    const float inv_n = 1.0f / (float)n_lights;
+    for (int i = 0; i < count; ++i)
+    {
+        const float r0 = rng.next_f();
+        const float r1 = rng.next_f();
+        const float r2 = rng.next_f();
+        const LightSample ls = sample_light(tris60, lights, n_lights, r0, r1, r2);
+        const float light_pdf = inv_n * 1.0f / ls.area;  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
+        const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
+        const float weight = p_hat / light_pdf;
+        const float u = rng.next_f();
+        r.w_sum += weight;  // Reservoir::update, reservoir.hpp:22-29
+        r.M += 1;
+        if (u < weight / r.w_sum)
+        {
+            r.s.hp = ls.p;
+            r.s.hn = ls.n;
+            r.s.rad = ls.emissive;
+            r.s.op = surf.p;
+            r.s.on = surf.n;
+            r.s.vis = 0;
+        }
+    }
+    return r;
+}
+
+// temporal_resampling body (10_restir_di.cu:172-233): `r` is this frame's reservoir, `prev` last frame's.
+template <class M>
+CRT_HD void temporal_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& opt, Res prev, Res& r, Pcg& rng)
+{
+    const int cap = 20 * opt.ris_count;  // M-cap, :186-188
+    prev.M = prev.M < cap ? prev.M : cap;
+    float p_hat_y = target_function(bvh, surf.p, surf.n, prev.s.hp, prev.s.hn, prev.s.rad, opt.shadowed);
+    if (opt.reuse) p_hat_y *= prev.s.vis ? 1.0f : 0.0f;
+    prev.M = f2i_trunc((float)prev.M * rejection_heuristics<M>(r.s, prev.s, eye));  // int *= float, :211-212
+    const float weight = p_hat_y * prev.ucw * (float)prev.M;
+    const float u = rng.next_f();
+    r.w_sum += weight;  // Reservoir::merge, reservoir.hpp:31-37
+    r.M += prev.M;
+    if (u < weight / r.w_sum) r.s = prev.s;
+    r.ucw = ucw_of(r, target_function(bvh, surf.p, surf.n, r.s.hp, r.s.hn, r.s.rad, opt.shadowed));
+}
+
+// one neighbour of spatial_resampling (10_restir_di.cu:340-370); compares against the *running* reservoir
+template <class M>
+CRT_HD void spatial_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& opt, Res nb, Res& r, Pcg& rng)
+{
+    float p_hat_y = target_function(bvh, surf.p, surf.n, nb.s.hp, nb.s.hn, nb.s.rad, opt.shadowed);
+    if (opt.reuse) p_hat_y *= nb.s.vis ? 1.0f : 0.0f;
+    nb.M = f2i_trunc((float)nb.M * rejection_heuristics<M>(r.s, nb.s, eye));
+    const float weight = p_hat_y * nb.ucw * (float)nb.M;
+    const float u = rng.next_f();  // third random only for neighbours that survive the rejections
+    r.w_sum += weight;
+    r.M += nb.M;
+    if (u < weight / r.w_sum) r.s = nb.s;
+}
+
+// neighbour pixel of spatial_resampling (10_restir_di.cu:309-313): two randoms, Box-Muller, truncation
+template <class M>
+CRT_HD void spatial_neighbour(int xi, int yi, float radius, Pcg& rng, int& x, int& y)
+{
+    const float rv0 = rng.next_f();
+    const float rv1 = rng.next_f();
+    const f2 g = sample_2d_gaussian<M>(rv0, rv1);
+    x = f2i_trunc((float)xi + radius / 1.96f * g.x);
+    y = f2i_trunc((float)yi + radius / 1.96f * g.y);
+}
+
+// resolve (10_restir_di.cu:431-447)
+CRT_HD f3 resolve_radiance(const Bvh& bvh, const Surf& surf, f3 color, const Res& r)
+{
+    const f3 brdf = kInvPi * color;
+    const float G = geometry_term(surf.p, surf.n, r.s.hp, r.s.hn);
+    const float V = check_visibility(bvh, surf.p, surf.n, r.s.hp);
+    return brdf * G * V * r.s.rad * r.ucw;
+}
+
+// tone mapping (common/kernels/common.cu:19-74)
+CRT_HD float aces(float x)
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    return (x * (a * x + b)) / (x * (c * x + d) + e);
+}
+CRT_HD uint32_t to_u8(float v)
+{
+    float s = v * 255.0f;
+    s = s > 0.0f ? s : 0.0f;  // max(x, 0): NaN -> 0
+    s = s < 255.0f ? s : 255.0f;
+    return (uint32_t)s;
+}
+template <class M>
+CRT_HD uint32_t tone_map_rgba8(f4 a)
+{
+    const float gamma = 1.0f / 2.2f;
+    const uint32_t r = to_u8(M::pow(aces(a.x / a.w), gamma));
+    const uint32_t g = to_u8(M::pow(aces(a.y / a.w), gamma));
+    const uint32_t b = to_u8(M::pow(aces(a.z / a.w), gamma));
+    return r | (g << 8) | (b << 16) | (255u << 24);
+}
+
+// next bounce (e.g. 08_nee.cu:98-106; core.hpp:209-235): tangent from edge v0->v1
+template <class M>
+CRT_HD f3 bounce_direction(const Surf& surf, const TriRef& tri, Pcg& rng)
+{
+    const f3 t = normalize(tri.v(1) - tri.v(0));
+    const f3 b = normalize(cross(t, surf.n));
+    const float r0 = rng.next_f();
+    const float r1 = rng.next_f();
+    const float r2 = rng.next_f();
+    const f3 l = sample_hemisphere<M>(r0, r1, r2);
+    return l.x * t + l.y * surf.n + l.z * b;
+}
+}  // namespace crt

@@ -1,0 +1,178 @@
+/* cedecrt.h — C ABI of libcedecrt.so: the B200 (sm_100a) drop-in for the ReSTIR DI hot path of
+ * yumcyaWiz/CEDEC-2024-RT (examples 06-10).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository).  All functions return 0 on success or a CRT_E* code; nothing throws, nothing traps
+ * (the reference ignores Orochi return codes or SIGTRAPs through SH_ASSERT, common/shader.hpp:10-16).
+ * There is no CPU fallback: without a CUDA device crt_init() fails with CRT_ENODEVICE.
+ *
+ * Struct layouts are the reference's, byte for byte (static_asserts in csrc/api.cu):
+ *   crt_triangle     common/core.hpp:38-43        60 B
+ *   crt_visibility   common/core.hpp:167-172      16 B
+ *   crt_reservoir    common/reservoir.hpp:5-38    76 B (sample 64 B)
+ *   crt_options      common/options.hpp:4-23      48 B
+ *   crt_raygen       common/camera.hpp:5-9        36 B
+ *   crt_buffer       common/typedbuffer.hpp:14-20 16 B  {T* data; size_t size:63, isDevice:1}
+ */
+#ifndef CEDECRT_H
+#define CEDECRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float x, y, z; } crt_float3;
+typedef struct { float x, y, z, w; } crt_float4;
+
+typedef struct { crt_float3 vertices[3]; crt_float3 color; crt_float3 emissive; } crt_triangle;
+typedef struct { float uv[2]; int32_t index; int32_t _pad; } crt_visibility;
+typedef struct
+{
+    crt_float3 origin_position, origin_normal, hit_position, hit_normal, radiance;
+    uint8_t visibility; /* C++ bool */
+    uint8_t _pad[3];
+} crt_reservoir_sample;
+typedef struct { crt_reservoir_sample sample; float w_sum; float ucw; int32_t M; } crt_reservoir;
+typedef struct
+{
+    uint8_t accumulate; uint8_t _p0[3];
+    int32_t max_depth;
+    crt_float3 sky_color;
+    int32_t ris_sample_count;
+    float rejection_heuristics_threshold; /* never read by any kernel, as in the reference */
+    uint8_t use_temporal_resampling;
+    uint8_t use_spatial_resampling; uint8_t _p1[2];
+    int32_t spatial_resampling_sample_count;
+    float spatial_resampling_radius;
+    int32_t spatial_resampling_passes; /* host-side loop count */
+    uint8_t use_shadowed_target_function;
+    uint8_t use_visibility_reuse; uint8_t _p2[2];
+} crt_options;
+typedef struct { crt_float3 m_origin, m_right, m_up; } crt_raygen;
+
+/* Device view of TypedBuffer<T> exactly as the reference passes it to kernels (ShaderArgument::ptr,
+ * common/shader.hpp:50-54,82-83): 16 bytes by value.  `size` counts elements; bit 63 is m_isDevice. */
+typedef struct { void* data; uint64_t size_and_flag; } crt_buffer;
+#define CRT_BUFFER_SIZE(b) ((b).size_and_flag & 0x7fffffffffffffffull)
+
+typedef struct crt_ctx crt_ctx;              /* one per GPU: device + stream (10_restir_di.cpp:30-53) */
+typedef struct crt_geometry_t* crt_geometry; /* opaque 8-byte handle in hiprtGeometry's argument slot */
+
+enum
+{
+    CRT_OK = 0,
+    CRT_ENODEVICE = 1, /* no CUDA device / driver: the library never computes on the CPU */
+    CRT_ECUDA = 2,     /* a CUDA runtime call failed; see crt_last_error() */
+    CRT_EINVAL = 3,    /* bad argument (null pointer, size mismatch, unknown kernel name) */
+    CRT_ENOMEM = 4,
+    CRT_ESTACK = 5     /* BVH deeper than the traversal stack */
+};
+
+/* numerics of the transcendental functions inside the kernels (log/sin/cos in the Gaussian neighbour
+ * draw, exp/pow in the rejection heuristics, pow in tone mapping and AO):
+ *   CRT_MATH_LIBDEVICE  CUDA's float functions — what the reference's NVRTC build computes. Default.
+ *   CRT_MATH_EXACT      correctly rounded via double; bit-identical to the CPU oracle's mode 1. */
+enum { CRT_MATH_LIBDEVICE = 0, CRT_MATH_EXACT = 1 };
+
+/* ---- context, memory, timing ------------------------------------------------------------------ */
+/* replaces oroInitialize/oroInit/oroDeviceGet/oroCtxCreate/oroStreamCreate (10_restir_di.cpp:30-53) */
+int crt_init(int device, crt_ctx** out);
+int crt_shutdown(crt_ctx* ctx);
+const char* crt_device_name(crt_ctx* ctx);  /* oroGetDeviceProperties().name (10_restir_di.cpp:47-52) */
+const char* crt_last_error(void);
+int crt_set_math_mode(crt_ctx* ctx, int mode);
+/* use an existing CUDA stream (e.g. torch's) instead of the context's own; NULL restores it */
+int crt_set_stream(crt_ctx* ctx, void* cuda_stream);
+void* crt_get_stream(crt_ctx* ctx);
+/* number of CUDA kernels this context has launched so far (bench.py reports it as gpu_launches) */
+unsigned long long crt_launch_count(crt_ctx* ctx);
+/* TypedBuffer<T>(DEVICE).allocate / dtor / toDevice / toHost (common/typedbuffer.hpp:29-77);
+ * memory is uninitialised, as with oroMalloc */
+int crt_malloc(crt_ctx* ctx, size_t bytes, void** out);
+int crt_free(crt_ctx* ctx, void* p);
+int crt_memset(crt_ctx* ctx, void* p, int byte, size_t bytes);
+int crt_memcpy_h2d(crt_ctx* ctx, void* dst, const void* src, size_t bytes);       /* oroMemcpyHtoD */
+int crt_memcpy_d2h(crt_ctx* ctx, void* dst, const void* src, size_t bytes);       /* oroMemcpyDtoH */
+int crt_memcpy_d2h_async(crt_ctx* ctx, void* dst, const void* src, size_t bytes); /* oroMemcpyDtoHAsync, :386 */
+int crt_sync(crt_ctx* ctx);                                                       /* oroStreamSynchronize, :389 */
+/* OroStopwatch (libs/orochi/Orochi/OrochiUtils.h:179-209): events on the context's stream */
+int crt_timer_start(crt_ctx* ctx);
+int crt_timer_stop_ms(crt_ctx* ctx, float* ms);
+
+/* RayGenerator::lookat (common/camera.hpp:11-25), evaluated on the host like the reference does */
+void crt_raygen_lookat(crt_raygen* rg, const float eye[3], const float center[3], const float up[3], float fovy,
+                       int width, int height);
+
+/* ---- geometry: replaces hiprtCreateContext + buildHiprtGeometry (10_restir_di.cpp:74-79,220;
+ * common/loader.hpp:68-112).  `triangles` is a DEVICE pointer to n reference Triangle structs; the
+ * BVH (compressed 8-wide nodes) is built on the GPU, synchronously.  The handle is passed by value
+ * to the kernels in hiprtGeometry's slot. */
+int crt_build_geometry(crt_ctx* ctx, const crt_triangle* d_triangles, size_t n, crt_geometry* out);
+int crt_destroy_geometry(crt_ctx* ctx, crt_geometry g);
+/* build statistics: {n_tris, n_wide_nodes, max_depth, build_ms, node_bytes, tri_bytes, sah_cost*1000} */
+int crt_geometry_stats(crt_geometry g, double out[8]);
+/* single-ray probes for tests (device arrays of n rays: origin, direction as float3, tmin/tmax);
+ * closest: out_prim (-1 = miss), out_tuv (t,u,v) — tie rule: smallest t, then largest primitive id
+ * (examples/04_ao/04_ao.cu:14-24).  any: out_prim = 1 if any hit in [tmin,tmax] else 0. */
+int crt_trace_closest(crt_ctx* ctx, crt_geometry g, size_t n, const float* d_org, const float* d_dir, float tmin,
+                      float tmax, int32_t* d_out_prim, float* d_out_tuv);
+int crt_trace_any(crt_ctx* ctx, crt_geometry g, size_t n, const float* d_org, const float* d_dir, float tmin,
+                  float tmax, int32_t* d_out_hit);
+/* same queries by exhaustive search over the triangle array with the reference's own test
+ * (common/core.hpp:91-136): the GPU-side check that the BVH only culls */
+int crt_trace_closest_brute(crt_ctx* ctx, const crt_triangle* d_triangles, size_t n_tris, size_t n,
+                            const float* d_org, const float* d_dir, float tmin, float tmax, int32_t* d_out_prim,
+                            float* d_out_tuv);
+
+/* ---- kernels: one export per reference KERNEL, parameter lists verbatim (same order, same by-value
+ * structs); grid/block are implied (the reference always launches ceil(W*H/256) x 256).
+ * Reservoir / Visibility buffers are the reference's AoS layouts ("drop-in mode"). */
+/* examples/10_restir_di/10_restir_di.cu:9-34 */
+int crt_raycast(crt_ctx* ctx, int width, int height, crt_geometry geom, crt_buffer triangles, crt_raygen raygen,
+                crt_buffer visibility_buffer);
+/* 10_restir_di.cu:36-135 */
+int crt_generate_candidate(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                           crt_buffer visibility_buffer, crt_float3 eye, crt_buffer lights, crt_options options,
+                           crt_buffer reservoirs);
+/* 10_restir_di.cu:137-237 */
+int crt_temporal_resampling(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                            crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                            crt_buffer previous_reservoirs, crt_buffer reservoirs);
+/* 10_restir_di.cu:239-254 — note the reference's parameter names are swapped: the first buffer is the source */
+int crt_save_temporal_reservoir(crt_ctx* ctx, int width, int height, crt_buffer src, crt_buffer dst);
+/* 10_restir_di.cu:256-388 */
+int crt_spatial_resampling(crt_ctx* ctx, int width, int height, int frame, int pass, crt_geometry geom,
+                           crt_buffer triangles, crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                           crt_buffer previous_reservoirs, crt_buffer reservoirs);
+/* 10_restir_di.cu:390-459 */
+int crt_resolve(crt_ctx* ctx, crt_buffer accumulation, int width, int height, crt_geometry geom,
+                crt_buffer triangles, crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                crt_buffer reservoirs);
+/* common/kernels/common.cu:4-17 and :30-74 */
+int crt_clear(crt_ctx* ctx, crt_buffer buffer, int width, int height);
+int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accumulation, int width, int height);
+/* examples/07_pt/07_pt.cu:11-15, 08_nee/08_nee.cu:11-15, 09_ris/09_ris.cu:11-15 */
+int crt_path_trace_07(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                      crt_raygen raygen, crt_options options, crt_buffer accumulation);
+int crt_path_trace_08(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                      crt_buffer lights, crt_raygen raygen, crt_options options, crt_buffer accumulation);
+int crt_path_trace_09(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                      crt_buffer lights, crt_raygen raygen, crt_options options, crt_buffer accumulation);
+/* examples/06_ao_hiprt/06_ao_hiprt.cu:35-37; n_rays replaces the hard-coded N_Rays = 64 (:71) */
+int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int width, int height, crt_geometry geom,
+              crt_buffer triangles, int n_rays);
+
+/* Shader::launch call shape (common/shader.hpp:179-199): kernel by name, params as the void*[] that
+ * ShaderArgument builds (pointers to by-value arguments, in order), grid/block accepted and ignored.
+ * Names: raycast, generate_candidate, temporal_resampling, save_temporal_reservoir, spatial_resampling,
+ * resolve, clear, tone_mapping (example 10); path_trace_07/08/09; ao_06 (its 7th param is int n_rays). */
+int crt_launch(crt_ctx* ctx, const char* name, void** params, unsigned gx, unsigned gy, unsigned gz, unsigned bx,
+               unsigned by, unsigned bz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEDECRT_H */
