@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py — ReSTIR DI 4K throughput (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 this repo's CUDA path
+  python bench.py --impl reference ...                                 the reference's own CPU implementation
+
+A "step" is one frame of the reference's frame loop (examples/10_restir_di/10_restir_di.cpp:229-380: raycast,
+generate_candidate, temporal_resampling, save_temporal_reservoir, 3 x spatial_resampling, resolve,
+tone_mapping) over BASELINE config 5: blocks_restir.obj tiled x6 (9 590 208 triangles, 875 892 lights),
+3840x2160, temporal + spatial (5 neighbours, r = 30, 3 passes) + visibility reuse, accumulate.
+
+value  = W*H*K / device time of the K frames (CUDA events, max over ranks), buffers resident in HBM —
+         the reference's own timing convention (OroStopwatch around the kernel list, 10_restir_di.cpp:254,382).
+e2e    = the same loop including, every frame, the device->host copy of the RGBA8 image into pinned host
+         memory (10_restir_di.cpp:386-389); the per-frame host inputs (RayGenerator, eye, Options) travel as
+         kernel parameters.
+N > 1  : the frame is split into horizontal row slabs, one rank per GPU (strong scaling); scene and BVH are
+         replicated, the reservoir/visibility halo rows the spatial passes read are exchanged with NCCL
+         send/recv between slab neighbours.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cedec-2024-rt_b200", "python"))
+
+W4K, H4K = 3840, 2160
+CAM = ((-0.579885, 22.194597, -6.567105), (5.224952, 20.847435, 1.431192))  # 10_restir_di.cpp:188-189
+HALO = 87  # |neighbour offset| <= 86.4 px (sample_2d_gaussian)
+# algorithmic bytes per pixel and kernel (reference struct sizes: Visibility 16,
+# Reservoir 76, float4 16, RGBA8 4; scene/BVH gathers and neighbour re-reads excluded)
+ALGO_BYTES = {"raycast": 16, "generate_candidate": 92, "temporal_resampling": 244, "save_temporal_reservoir": 152,
+              "spatial_resampling": 168, "resolve": 124, "tone_mapping": 20}
+RESERVOIR_PASSES = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampling", "resolve")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_workload():
+    """BASELINE config 5 scene; falls back to a procedural scene of the same character if the asset cache
+    (assets/blocks_restir.tri.xz, staged by oracle/stage_assets.py) is absent, and says so."""
+    import scenes
+
+    if scenes.find_scene("blocks_restir"):
+        base = scenes.load_scene("blocks_restir")
+        return scenes.tile_scene(base, 3, 2, 130.0, 82.0), CAM, "10_restir_di: blocks_restir.obj tiled x6 (3x2, pitch 130/82)"
+    tris = scenes.procedural_blocks(n_blocks=800000, seed=1, extent=200.0)
+    return tris, ((0.0, 22.0, 0.0), (30.0, 18.0, 30.0)), "10_restir_di: PROCEDURAL stand-in scene (blocks_restir cache not staged)"
+
+
+def slab_rows(H, world, rank):
+    """row slabs of yi, balanced to multiples of 8 rows (the kernels' tile height)"""
+    edges = [((H * r // world) + 7) // 8 * 8 for r in range(world)] + [H]
+    edges[0] = 0
+    return edges[rank], edges[rank + 1]
+
+
+# ============================================================================================== CUDA arm
+class SlabRenderer:
+    """The frame loop over one GPU's row slab.  Buffers are full-size (pixel indices stay global) and are torch
+    tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
+
+    def __init__(self, torch, dist, rank, world, tris, cam, W, H):
+        import numpy as np
+
+        import cedecrt
+
+        self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
+        self.c = cedecrt
+        self.rt = cedecrt.Runtime(torch.cuda.current_device())
+        self.rt.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.y0, self.y1 = slab_rows(H, world, rank)
+        self.rt.set_row_range(self.y0, self.y1)
+        self.options = cedecrt.Options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+        self.eye = tuple(float(np.float32(v)) for v in cam[0])
+        self.raygen = cedecrt.lookat(cam[0], cam[1], W, H)
+        n = W * H
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def tbuf(nbytes, dtype, count, zero=False):
+            t = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
+            return t, self.rt.wrap(t.data_ptr(), dtype, count)
+
+        self.t_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).to(dev)
+        self.triangles = self.rt.wrap(self.t_tris.data_ptr(), cedecrt.TRIANGLE, len(tris))
+        lights = cedecrt.light_indices(tris)
+        self.t_lights = torch.from_numpy(lights.view(np.uint8)).to(dev)
+        self.lights = self.rt.wrap(self.t_lights.data_ptr(), np.uint32, len(lights))
+        self.n_tris, self.n_lights = len(tris), len(lights)
+        self.geom = self.rt.build_geometry(self.triangles)
+        self.t_pix, self.pixels = tbuf(4 * n, np.uint8, 4 * n)
+        self.t_acc, self.accumulation = tbuf(16 * n, cedecrt.FLOAT4, n, zero=True)
+        self.t_vis, self.visibility = tbuf(16 * n, cedecrt.VISIBILITY, n, zero=True)
+        self.t_r0, self.reservoir0 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
+        self.t_r1, self.reservoir1 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
+        self.t_tmp, self.temporal = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
+        self.host_pixels = torch.empty(4 * W * (self.y1 - self.y0), dtype=torch.uint8).pin_memory()
+        self.frame_index = 0
+        self.kernel_ms = None
+
+    # ---- halo exchange: rows [a, b) of yi are the byte range [(H-b)*W, (H-a)*W) * elem of a bottom-up buffer
+    def _rows(self, t, elem, a, b):
+        return t[(self.H - b) * self.W * elem:(self.H - a) * self.W * elem]
+
+    def exchange_halo(self, t, elem):
+        """send my boundary rows to the slab neighbours, receive theirs into the same global positions"""
+        if self.world == 1:
+            return 0
+        ops, dist, nbytes = [], self.dist, 0
+        for nb, mine, theirs in ((self.rank - 1, (self.y0, min(self.y0 + HALO, self.y1)), (max(self.y0 - HALO, 0), self.y0)),
+                                 (self.rank + 1, (max(self.y1 - HALO, self.y0), self.y1), (self.y1, min(self.y1 + HALO, self.H)))):
+            if nb < 0 or nb >= self.world:
+                continue
+            # the neighbour needs HALO of my rows; I need HALO of its rows (slabs are taller than HALO here)
+            ops.append(dist.P2POp(dist.isend, self._rows(t, elem, *mine), nb))
+            ops.append(dist.P2POp(dist.irecv, self._rows(t, elem, *theirs), nb))
+            nbytes += (mine[1] - mine[0]) * self.W * elem
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        return nbytes
+
+    def frame(self, timers=None):
+        rt, W, H, o, g, t, v, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.visibility, self.eye
+        self.frame_index += 1
+        f = self.frame_index
+
+        def run(name, fn, *a):
+            if timers is None:
+                fn(*a)
+            else:
+                e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(*a)
+                e1.record()
+                timers.append((name, e0, e1))
+
+        run("raycast", rt.raycast, W, H, g, t, self.raygen, v)
+        self.exchange_halo(self.t_vis, 16)
+        run("generate_candidate", rt.generate_candidate, W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
+        run("temporal_resampling", rt.temporal_resampling, W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        run("save_temporal_reservoir", rt.save_temporal_reservoir, W, H, self.reservoir0, self.temporal)
+        bi, bo, ti = self.reservoir0, self.reservoir1, self.t_r0
+        for k in range(o.spatial_resampling_passes):
+            if k != 0:
+                bi, bo = bo, bi
+                ti = self.t_r1 if ti is self.t_r0 else self.t_r0
+            self.exchange_halo(ti, 76)
+            run("spatial_resampling", rt.spatial_resampling, W, H, f, k, g, t, v, eye, o, bi, bo)
+        run("resolve", rt.resolve, self.accumulation, W, H, g, t, v, eye, o, bo)
+        run("tone_mapping", rt.tone_mapping, self.pixels, self.accumulation, W, H)
+
+    def download_pixels(self):
+        src = self._rows(self.t_pix, 4, self.y0, self.y1)
+        self.host_pixels.copy_(src, non_blocking=True)
+
+
+def rays_per_frame(torch, r):
+    """rays actually traced in one frame of config 5: 1 primary per pixel + 2 shadow rays
+    (visibility reuse, resolve) per pixel whose primary hit is a non-emissive surface; counted from the
+    visibility buffer of this rank's slab."""
+    import numpy as np
+
+    vis = r._rows(r.t_vis, 16, r.y0, r.y1).view(torch.int32).reshape(-1, 4)[:, 2]
+    em = r.t_tris.view(torch.float32).reshape(-1, 15)[:, 12:15]
+    is_em = (em > 0).any(1)
+    hit = vis >= 0
+    diffuse = hit.clone()
+    diffuse[hit] = ~is_em[vis[hit].long()]
+    n_px = r.W * (r.y1 - r.y0)
+    return n_px + 2 * int(diffuse.sum().item())
+
+
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tris, cam, workload = load_workload()
+    W, H = args.width, args.height
+    r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H)
+    stats = r.geom.stats()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        r.frame()
+    barrier()
+    launches0 = r.rt.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: K frames, resident buffers
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        r.frame()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = r.rt.launch_count() - launches0
+    # ---- timed: K frames end to end (per-frame D2H of the RGBA8 image into pinned host memory)
+    barrier()
+    t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e0.record()
+    for _ in range(args.steps):
+        r.frame()
+        r.download_pixels()
+        torch.cuda.current_stream().synchronize()  # oroStreamSynchronize after the copy (10_restir_di.cpp:389)
+    t_e1.record()
+    barrier()
+    ms_e2e = t_e0.elapsed_time(t_e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- per-kernel device times (instrumented frames, outside the timed regions)
+    timers = []
+    for _ in range(max(2, min(args.steps, 4))):
+        r.frame(timers)
+    torch.cuda.synchronize()
+    per_kernel = {}
+    for name, a, b in timers:
+        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
+    rays = rays_per_frame(torch, r)
+
+    t = torch.tensor([ms, ms_e2e, float(rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e, rays = tmax[0].item(), tmax[1].item(), tsum[2].item()
+    if rank == 0:
+        n_px = W * H
+        peak, peak_src = measured_peaks()
+        my_px = W * (r.y1 - r.y0)
+        kern = {}
+        for name, ts in per_kernel.items():
+            per_launch = sum(ts) / len(ts)
+            kern[name] = {"ms_per_launch": round(per_launch, 4), "launches_per_frame": len(ts) // max(2, min(args.steps, 4)),
+                          "algo_bytes_per_px": ALGO_BYTES[name],
+                          "algo_gbs": round(ALGO_BYTES[name] * my_px / per_launch / 1e6, 1)}
+        frame_ms_by_kernel = {k: v["ms_per_launch"] * v["launches_per_frame"] for k, v in kern.items()}
+        dominant = max(frame_ms_by_kernel, key=frame_ms_by_kernel.get)
+        res_bytes = sum(ALGO_BYTES[k] * kern[k]["launches_per_frame"] for k in RESERVOIR_PASSES) * my_px
+        res_ms = sum(frame_ms_by_kernel[k] for k in RESERVOIR_PASSES)
+        out = {
+            "metric": "ReSTIR DI 4K Mpix/s", "value": round(n_px * args.steps / ms / 1e3, 3), "unit": "Mpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "width": W, "height": H, "triangles": r.n_tris, "lights": r.n_lights,
+                       "options": "temporal+spatial(5 nbrs, r=30, 3 passes)+visibility reuse, accumulate, ris 32",
+                       "camera": "10_restir_di.cpp:188-189", "partition": "%d row slab(s), halo %d rows" % (world, HALO),
+                       "l2": "per-frame working set (3 x 630 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
+                       "math": "libdevice float (reference NVRTC semantics), -fmad=false"},
+            "grays_per_s": round(rays * args.steps / ms / 1e6, 4), "rays_per_frame": int(rays),
+            "e2e": {"value": round(n_px * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s",
+                    "h2d_bytes_per_step": 96, "d2h_bytes_per_step": 4 * n_px,
+                    "note": "per-frame inputs (RayGenerator 36 B, eye 12 B, Options 48 B) go as kernel parameters; "
+                            "the RGBA8 frame is copied to pinned host memory every step"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": dominant, "bound": "hbm",
+                         "achieved": kern[dominant]["algo_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": round(kern[dominant]["algo_gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "note": "dominant kernel by time; traversal kernels are latency/cache-bound, see profiles/"},
+            "roofline_reservoir_passes": {"bound": "hbm", "achieved": round(res_bytes / res_ms / 1e6, 1), "peak": peak,
+                                          "unit": "GB/s", "frac": round(res_bytes / res_ms / 1e6 / peak, 4),
+                                          "kernels": list(RESERVOIR_PASSES)},
+            "kernels": kern,
+            "bvh": {k: stats[k] for k in ("n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample(r, tris, cam, W, H)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ============================================================================================== CPU arms
+def cpu_band_run(o, tris, cam, W, H, rows, frames, bufs=None):
+    """one bounded sample of the workload on the CPU oracle: every kernel of the frame loop restricted to a
+    band of `rows` image rows (orc_set_range); full-size zero-initialised buffers.  Returns seconds per kernel."""
+    import numpy as np
+
+    import orc
+
+    y0 = (H - rows) // 2
+    o.set_range(y0 * W, (y0 + rows) * W)
+    opt = orc.make_options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    n = W * H
+    if bufs is None:
+        bufs = dict(vis=np.zeros(n, orc.VISIBILITY), r0=np.zeros(n, orc.RESERVOIR), r1=np.zeros(n, orc.RESERVOIR),
+                    tmp=np.zeros(n, orc.RESERVOIR), acc=np.zeros((n, 4), np.float32), pix=np.zeros(4 * n, np.uint8))
+        bufs["vis"]["index"] = -1
+    g = bufs.get("geom") or o.geom_build(tris)
+    bufs["geom"] = g
+    rg = o.lookat(cam[0], cam[1], W, H)
+    lights = orc.light_indices(tris)
+    eye = np.asarray(cam[0], np.float32)
+    times = {}
+
+    def run(name, fn, *a):
+        t0 = time.perf_counter()
+        fn(*a)
+        times[name] = times.get(name, 0.0) + time.perf_counter() - t0
+
+    for f in frames:
+        run("raycast", o.raycast, W, H, g, tris, rg, bufs["vis"])
+        run("generate_candidate", o.generate_candidate, W, H, f, g, tris, bufs["vis"], eye, lights, opt, bufs["r0"])
+        run("temporal_resampling", o.temporal_resampling, W, H, f, g, tris, bufs["vis"], eye, opt, bufs["tmp"], bufs["r0"])
+        run("save_temporal_reservoir", o.save_temporal_reservoir, W, H, bufs["r0"], bufs["tmp"])
+        bi, bo = bufs["r0"], bufs["r1"]
+        for k in range(3):
+            if k:
+                bi, bo = bo, bi
+            run("spatial_resampling", o.spatial_resampling, W, H, f, k, g, tris, bufs["vis"], eye, opt, bi, bo)
+        run("resolve", o.resolve, bufs["acc"], W, H, g, tris, bufs["vis"], eye, opt, bo)
+        run("tone_mapping", o.tone_mapping, bufs["acc"], W, H, bufs["pix"])
+    o.set_range(0, -1)
+    return times, bufs
+
+
+def load_cpu_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+
+    if orc.have_reference():
+        return orc.load("reference", 10), "reference"
+    return orc.load("port"), "port"
+
+
+def cpu_baseline_sample(r, tris, cam, W, H, rows=64):
+    """cpu_baseline of the CUDA arm's JSON line: the reference's CPU implementation timed on this box's host cores
+    on a bounded sample (a band of rows of the same frame)."""
+    o, kind = load_cpu_oracle()
+    times, _ = cpu_band_run(o, tris, cam, W, H, rows, frames=[1])
+    sec = sum(times.values())
+    return {"value": round(rows * W / sec / 1e6, 4), "unit": "Mpix/s", "cores": o.threads(), "kind": kind,
+            "sample": "frame 1, image rows %d..%d of the %dx%d frame (%d px), all 9 kernel launches of the frame loop, "
+                      "OpenMP over pixels; BVH build excluded" % ((H - rows) // 2, (H - rows) // 2 + rows, W, H, rows * W),
+            "seconds": round(sec, 3), "seconds_by_kernel": {k: round(v, 3) for k, v in times.items()}}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: its unmodified kernels as
+    host C++ with OpenMP; else the port), all host threads, same config; each step = one frame of a bounded band."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    o, kind = load_cpu_oracle()
+    tris, cam, workload = load_workload()
+    W, H, rows = args.width, args.height, args.cpu_rows
+    bufs = None
+    frame = 0
+    for _ in range(args.warmup):
+        frame += 1
+        _, bufs = cpu_band_run(o, tris, cam, W, H, rows, [frame], bufs)
+    t0 = time.perf_counter()
+    per_kernel = {}
+    for _ in range(args.steps):
+        frame += 1
+        times, bufs = cpu_band_run(o, tris, cam, W, H, rows, [frame], bufs)
+        for k, v in times.items():
+            per_kernel[k] = per_kernel.get(k, 0.0) + v
+    sec = sum(per_kernel.values())
+    wall = time.perf_counter() - t0
+    value = round(rows * W * args.steps / sec / 1e6, 4)
+    sample = ("each step = one frame over image rows %d..%d of the %dx%d frame (%d px), all kernels of the frame loop; "
+              "BVH build excluded" % ((H - rows) // 2, (H - rows) // 2 + rows, W, H, rows * W))
+    print(json.dumps({
+        "impl": "reference", "metric": "ReSTIR DI 4K Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "width": W, "height": H, "triangles": int(len(tris)),
+                   "options": "temporal+spatial(5 nbrs, r=30, 3 passes)+visibility reuse, accumulate, ris 32",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": o.threads(), "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(wall, 2),
+        "seconds_by_kernel": {k: round(v, 3) for k, v in per_kernel.items()},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--cpu-rows", type=int, default=64, help="band height of the CPU arm's per-step sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

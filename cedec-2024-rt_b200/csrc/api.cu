@@ -72,6 +72,15 @@ extern "C" int crt_set_math_mode(crt_ctx* ctx, int mode)
     return CRT_OK;
 }
 
+extern "C" int crt_set_row_range(crt_ctx* ctx, int y_begin, int y_end)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_REQUIRE(y_begin >= 0 && (y_end < 0 || y_end >= y_begin), "bad row range");
+    ctx->row_begin = y_begin;
+    ctx->row_end = y_end;
+    return CRT_OK;
+}
+
 extern "C" int crt_set_stream(crt_ctx* ctx, void* cuda_stream)
 {
     CRT_REQUIRE(ctx, "null context");

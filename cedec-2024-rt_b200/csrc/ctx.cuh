@@ -17,6 +17,7 @@ struct crt_ctx
     int math_mode = CRT_MATH_LIBDEVICE;
     int sm_count = 0;
     char name[256] = {0};
+    int row_begin = 0, row_end = -1;  // rows of yi this context computes (crt_set_row_range); -1 = image height
     unsigned long long launches = 0;  // kernels launched through this context (bench.py: gpu_launches)
 };
 

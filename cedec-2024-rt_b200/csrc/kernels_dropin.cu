@@ -20,33 +20,49 @@ struct TilePix
     Pix px;
     bool in;
 };
-__device__ __forceinline__ TilePix this_pixel(int W, int H)
+// rows [y0, y1) of the image are processed (multi-GPU row slabs: crt_set_row_range); pixel coordinates stay global
+struct Rows
+{
+    int y0, y1;
+};
+__device__ __forceinline__ TilePix this_pixel(int W, int H, Rows rows)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int xi = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
-    const int yi = blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
-    return {make_pix(xi, yi, W, H), xi < W && yi < H};
+    const int yi = rows.y0 + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
+    return {make_pix(xi, yi, W, H), xi < W && yi < rows.y1};
 }
-static dim3 tile_grid(int W, int H) { return dim3((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH); }
-
-__global__ void __launch_bounds__(256) k_raycast(int W, int H, Bvh bvh, crt_raygen raygen, crt_visibility* vis)
+static dim3 tile_grid(int W, Rows r)
 {
-    const TilePix t = this_pixel(W, H);
+    const int ny = (r.y1 - r.y0 + kTileH - 1) / kTileH;
+    return dim3((W + kTileW - 1) / kTileW, ny > 0 ? ny : 1);  // an empty slab still launches one (idle) row of tiles
+}
+static Rows rows_of(const crt_ctx* ctx, int H)
+{
+    Rows r{ctx->row_begin, ctx->row_end < 0 || ctx->row_end > H ? H : ctx->row_end};
+    if (r.y0 < 0) r.y0 = 0;
+    if (r.y0 > r.y1) r.y0 = r.y1;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_raycast(int W, int H, Rows rows, Bvh bvh, crt_raygen raygen, crt_visibility* vis)
+{
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in) px_raycast(t.px, W, H, bvh, raygen, vis);
 }
 __global__ void __launch_bounds__(256)
-    k_generate_candidate(int W, int H, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+    k_generate_candidate(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
                          const uint32_t* lights, uint32_t n_lights, crt_options options, crt_reservoir* out)
 {
-    const TilePix t = this_pixel(W, H);
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in) px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, n_lights, make_opt(options), AosStore{out});
 }
 template <int MODE>
 __global__ void __launch_bounds__(256)
-    k_temporal(int W, int H, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+    k_temporal(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
                crt_options options, const crt_reservoir* prev, crt_reservoir* cur)
 {
-    const TilePix t = this_pixel(W, H);
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in)
         px_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, make_opt(options),
                                 AosStore{const_cast<crt_reservoir*>(prev)}, AosStore{cur});
@@ -60,19 +76,19 @@ __global__ void __launch_bounds__(256) k_save_temporal(size_t n_words, const uin
 }
 template <int MODE>
 __global__ void __launch_bounds__(256)
-    k_spatial(int W, int H, int frame, int pass, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+    k_spatial(int W, int H, Rows rows, int frame, int pass, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
               crt_options options, const crt_reservoir* in, crt_reservoir* out)
 {
-    const TilePix t = this_pixel(W, H);
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in)
         px_spatial<Math<MODE>>(t.px, W, H, frame, pass, bvh, tris60, vis, eye, make_opt(options),
                                AosStore{const_cast<crt_reservoir*>(in)}, AosStore{out});
 }
 __global__ void __launch_bounds__(256)
-    k_resolve(crt_float4* accum, int W, int H, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+    k_resolve(crt_float4* accum, int W, int H, Rows rows, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
               crt_options options, const crt_reservoir* res)
 {
-    const TilePix t = this_pixel(W, H);
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in) px_resolve(t.px, accum, bvh, tris60, vis, eye, make_opt(options), AosStore{const_cast<crt_reservoir*>(res)});
 }
 
@@ -93,18 +109,18 @@ __global__ void __launch_bounds__(256) k_tone_mapping(size_t n, uint32_t* pixels
 }
 template <int EX, int MODE>
 __global__ void __launch_bounds__(256)
-    k_path_trace(int W, int H, int frame, Bvh bvh, const float* tris60, const uint32_t* lights, uint32_t n_lights,
+    k_path_trace(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const uint32_t* lights, uint32_t n_lights,
                  crt_raygen raygen, crt_options options, crt_float4* accum)
 {
-    const TilePix t = this_pixel(W, H);
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in)
         px_path_trace<EX, Math<MODE>>(t.px, W, H, frame, bvh, tris60, lights, n_lights, raygen, make_opt(options), accum);
 }
 template <int MODE>
 __global__ void __launch_bounds__(256)
-    k_ao(uint32_t* pixels, crt_raygen raygen, int W, int H, Bvh bvh, const float* tris60, int n_rays)
+    k_ao(uint32_t* pixels, crt_raygen raygen, int W, int H, Rows rows, Bvh bvh, const float* tris60, int n_rays)
 {
-    const TilePix t = this_pixel(W, H);
+    const TilePix t = this_pixel(W, H, rows);
     if (t.in) pixels[t.px.idx] = px_ao<Math<MODE>>(t.px, raygen, W, H, bvh, tris60, n_rays);
 }
 }  // namespace crt
@@ -133,7 +149,7 @@ extern "C" int crt_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_bu
     CRT_CHECK_IMAGE(W, H);
     CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
     (void)triangles;  // the reference's raycast does not read it either (10_restir_di.cu:9-34)
-    k_raycast<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, geom->view(), raygen,
+    k_raycast<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), geom->view(), raygen,
                                                        (crt_visibility*)visibility_buffer.data);
     return check_launch(ctx, "raycast");
 }
@@ -149,8 +165,8 @@ extern "C" int crt_generate_candidate(crt_ctx* ctx, int W, int H, int frame, crt
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
     CRT_REQUIRE(bsize(lights) < 0xffffffffull, "too many lights");
-    k_generate_candidate<<<tile_grid(W, H), 256, 0, ctx->stream>>>(
-        W, H, frame, geom->view(), (const float*)triangles.data, (const crt_visibility*)visibility_buffer.data,
+    k_generate_candidate<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(
+        W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data, (const crt_visibility*)visibility_buffer.data,
         to_f3(eye), (const uint32_t*)lights.data, (uint32_t)bsize(lights), options, (crt_reservoir*)reservoirs.data);
     return check_launch(ctx, "generate_candidate");
 }
@@ -166,7 +182,7 @@ extern "C" int crt_temporal_resampling(crt_ctx* ctx, int W, int H, int frame, cr
     CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_temporal<1> : k_temporal<0>;
-    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, frame, geom->view(), (const float*)triangles.data,
+    k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data,
                                                (const crt_visibility*)visibility_buffer.data, to_f3(eye), options,
                                                (const crt_reservoir*)previous_reservoirs.data,
                                                (crt_reservoir*)reservoirs.data);
@@ -179,9 +195,13 @@ extern "C" int crt_save_temporal_reservoir(crt_ctx* ctx, int W, int H, crt_buffe
     CRT_CHECK_IMAGE(W, H);
     CRT_CHECK_BUF(src, (size_t)W * H, "source reservoir");
     CRT_CHECK_BUF(dst, (size_t)W * H, "destination reservoir");
-    const size_t n_words = (size_t)W * H * (sizeof(crt_reservoir) / 4);
-    k_save_temporal<<<sweep_blocks(ctx, n_words), 256, 0, ctx->stream>>>(n_words, (const uint32_t*)src.data,
-                                                                        (uint32_t*)dst.data);
+    // rows [y0,y1) are the contiguous pixel range [(H-y1)*W, (H-y0)*W) of the bottom-up buffers
+    const Rows r = rows_of(ctx, H);
+    const size_t wpp = sizeof(crt_reservoir) / 4, first = (size_t)(H - r.y1) * W * wpp;
+    const size_t n_words = (size_t)(r.y1 - r.y0) * W * wpp;
+    if (n_words == 0) return CRT_OK;
+    k_save_temporal<<<sweep_blocks(ctx, n_words), 256, 0, ctx->stream>>>(n_words, (const uint32_t*)src.data + first,
+                                                                        (uint32_t*)dst.data + first);
     return check_launch(ctx, "save_temporal_reservoir");
 }
 
@@ -197,7 +217,7 @@ extern "C" int crt_spatial_resampling(crt_ctx* ctx, int W, int H, int frame, int
     CRT_REQUIRE(previous_reservoirs.data != reservoirs.data, "spatial_resampling cannot run in place");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_spatial<1> : k_spatial<0>;
-    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, frame, pass, geom->view(), (const float*)triangles.data,
+    k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, pass, geom->view(), (const float*)triangles.data,
                                                (const crt_visibility*)visibility_buffer.data, to_f3(eye), options,
                                                (const crt_reservoir*)previous_reservoirs.data,
                                                (crt_reservoir*)reservoirs.data);
@@ -214,7 +234,7 @@ extern "C" int crt_resolve(crt_ctx* ctx, crt_buffer accumulation, int W, int H, 
     CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
     CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
-    k_resolve<<<tile_grid(W, H), 256, 0, ctx->stream>>>((crt_float4*)accumulation.data, W, H, geom->view(),
+    k_resolve<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>((crt_float4*)accumulation.data, W, H, rows_of(ctx, H), geom->view(),
                                                        (const float*)triangles.data,
                                                        (const crt_visibility*)visibility_buffer.data, to_f3(eye),
                                                        options, (const crt_reservoir*)reservoirs.data);
@@ -226,8 +246,10 @@ extern "C" int crt_clear(crt_ctx* ctx, crt_buffer buffer, int W, int H)
     CRT_REQUIRE(ctx, "null context");
     CRT_CHECK_IMAGE(W, H);
     CRT_CHECK_BUF(buffer, (size_t)W * H, "accumulation");
-    const size_t n = (size_t)W * H;
-    k_clear<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (float4*)buffer.data);
+    const Rows r = rows_of(ctx, H);
+    const size_t n = (size_t)(r.y1 - r.y0) * W, first = (size_t)(H - r.y1) * W;
+    if (n == 0) return CRT_OK;
+    k_clear<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (float4*)buffer.data + first);
     return check_launch(ctx, "clear");
 }
 
@@ -237,9 +259,12 @@ extern "C" int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accu
     CRT_CHECK_IMAGE(W, H);
     CRT_CHECK_BUF(pixels, (size_t)W * H * 4, "pixel");
     CRT_CHECK_BUF(accumulation, (size_t)W * H, "accumulation");
-    const size_t n = (size_t)W * H;
+    const Rows r = rows_of(ctx, H);
+    const size_t n = (size_t)(r.y1 - r.y0) * W, first = (size_t)(H - r.y1) * W;
+    if (n == 0) return CRT_OK;
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_tone_mapping<1> : k_tone_mapping<0>;
-    k<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (uint32_t*)pixels.data, (const float4*)accumulation.data);
+    k<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (uint32_t*)pixels.data + first,
+                                                    (const float4*)accumulation.data + first);
     return check_launch(ctx, "tone_mapping");
 }
 
@@ -253,7 +278,7 @@ static int path_trace(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, 
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(EX == 7 || bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_path_trace<EX, 1> : k_path_trace<EX, 0>;
-    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>(W, H, frame, geom->view(), (const float*)triangles.data,
+    k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data,
                                                (const uint32_t*)lights.data, (uint32_t)bsize(lights), raygen, options,
                                                (crt_float4*)accumulation.data);
     return check_launch(ctx, "path_trace");
@@ -283,7 +308,7 @@ extern "C" int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(n_rays > 0, "n_rays must be positive");
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_ao<1> : k_ao<0>;
-    k<<<tile_grid(W, H), 256, 0, ctx->stream>>>((uint32_t*)pixels.data, raygen, W, H, geom->view(),
+    k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>((uint32_t*)pixels.data, raygen, W, H, rows_of(ctx, H), geom->view(),
                                                (const float*)triangles.data, n_rays);
     return check_launch(ctx, "ao_06");
 }

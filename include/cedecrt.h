@@ -84,6 +84,10 @@ int crt_shutdown(crt_ctx* ctx);
 const char* crt_device_name(crt_ctx* ctx);  /* oroGetDeviceProperties().name (10_restir_di.cpp:47-52) */
 const char* crt_last_error(void);
 int crt_set_math_mode(crt_ctx* ctx, int mode);
+/* Multi-GPU row slabs: the kernels of this context compute only image rows yi in [y_begin, y_end) (y_end < 0:
+ * to the image height).  Pixel coordinates, RNG keys and buffer indices stay global, so N slabs give exactly
+ * the single-GPU frame; buffers are full-size and the host exchanges the halo rows the spatial pass reads. */
+int crt_set_row_range(crt_ctx* ctx, int y_begin, int y_end);
 /* use an existing CUDA stream (e.g. torch's) instead of the context's own; NULL restores it */
 int crt_set_stream(crt_ctx* ctx, void* cuda_stream);
 void* crt_get_stream(crt_ctx* ctx);

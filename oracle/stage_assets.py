@@ -1,7 +1,7 @@
 """TEST/BENCH INFRASTRUCTURE — stages the reference's scenes as binary Triangle[] caches.
 
 The GPU box has no /root/reference, so the scenes travel with the repo snapshot as git-ignored files under
-oracle/_ref/assets/<name>.tri.xz: the exact bytes of the reference loader's std::vector<Triangle>
+assets/<name>.tri.xz: the exact bytes of the reference loader's std::vector<Triangle>
 (common/loader.hpp:11-66 + tinyobjloader 1.0.6, run through oracle/_ref/libref_loader.so), LZMA-compressed.
 Nothing is committed; rerun here whenever oracle/_ref is rebuilt:   python oracle/stage_assets.py
 """
@@ -17,7 +17,7 @@ sys.path.insert(0, HERE)
 import orc  # noqa: E402
 
 ASSETS = "/root/reference/assets/"
-OUT = os.path.join(HERE, "_ref", "assets")
+OUT = os.path.join(HERE, "..", "assets")
 SCENES = ("cornellbox1", "blocks_ao", "blocks_pt", "blocks_restir")
 
 

@@ -1,0 +1,155 @@
+"""Logic of the CUDA path, checked without a GPU: tests/emu compiles the device functions of
+cedec-2024-rt_b200/csrc/*.cuh (BVH build steps, wide-BVH walk, every per-pixel body) for the host and these
+tests compare them bit for bit with the oracle (canonical left-to-right argument order, both math modes).
+The real parity tests — the CUDA kernels through the C ABI — are in test_gpu_parity.py (-m gpu)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from helpers import reservoir_mismatch, same, small_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CAM_CB = ((0.0, 2.7, 9.0), (0.0, 2.7, 0.0))
+CAM_AO = ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(ROOT, "tests", "emu", "libemu.so")
+    src = os.path.join(ROOT, "tests", "emu", "emu.cpp")
+    inc = os.path.join(ROOT, "cedec-2024-rt_b200", "csrc")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-std=c++17", "-O2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                    "-I" + inc, "-o", so, src], check=True)
+    return orc.Oracle(so)
+
+
+def lit_blocks_ao():
+    t = small_scene("blocks_ao").copy()
+    t["emissive"][100:140] = (5.0, 4.0, 3.0)
+    return t
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("scene", ["cornellbox1", "blocks_ao_lit"])
+def test_restir_chain(emu, port, scene, mode):
+    tris = small_scene("cornellbox1") if scene == "cornellbox1" else lit_blocks_ao()
+    cam, (W, H) = (CAM_CB, (96, 54)) if scene == "cornellbox1" else (CAM_AO, (128, 72))
+    opt = orc.make_options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    outs = []
+    for o in (port, emu):
+        o.set_math_mode(mode)
+        g = o.geom_build(tris)
+        ch = orc.RestirChain(o, W, H, tris, g, *cam, opt)
+        for _ in range(3):
+            ch.step()
+        outs.append((ch.vis.copy(), ch.buf0.copy(), ch.buf1.copy(), ch.temporal.copy(), ch.accum.copy(),
+                     o.tone_mapping(ch.accum, W, H).copy()))
+        o.geom_free(g)
+        o.set_math_mode(0)
+    a, b = outs
+    assert same(a[0]["index"], b[0]["index"]) and same(a[0]["uv"], b[0]["uv"])
+    for k in (1, 2, 3):
+        assert reservoir_mismatch(a[k], b[k]) == 0
+    assert same(a[4], b[4]) and same(a[5], b[5].view(np.uint8))
+    assert float(a[4][:, :3].sum()) > 0
+
+
+def test_option_variants(emu, port):
+    tris = small_scene("cornellbox1")
+    W, H = 64, 36
+    for kw in (dict(use_shadowed_target_function=1, use_visibility_reuse=0, use_temporal_resampling=1,
+                    use_spatial_resampling=1, ris_sample_count=8, spatial_resampling_passes=2),
+               dict(use_spatial_resampling=0, use_temporal_resampling=1),
+               dict(use_spatial_resampling=1, use_temporal_resampling=0, spatial_resampling_radius=5.0,
+                    spatial_resampling_sample_count=2, accumulate=1)):
+        opt = orc.make_options(**kw)
+        outs = []
+        for o in (port, emu):
+            g = o.geom_build(tris)
+            ch = orc.RestirChain(o, W, H, tris, g, *CAM_CB, opt)
+            ch.step()
+            ch.step()
+            outs.append((ch.buf0.copy(), ch.buf1.copy(), ch.accum.copy()))
+            o.geom_free(g)
+        assert reservoir_mismatch(outs[0][0], outs[1][0]) == 0 and reservoir_mismatch(outs[0][1], outs[1][1]) == 0
+        assert same(outs[0][2], outs[1][2]), kw
+
+
+@pytest.mark.parametrize("ex", [7, 8, 9])
+def test_path_tracers(emu, port, ex):
+    tris = small_scene("cornellbox1")
+    W, H = 64, 36
+    opt = orc.make_options(accumulate=1, max_depth=4, ris_sample_count=8, sky_color=(0.1, 0.2, 0.3))
+    lights = orc.light_indices(tris)
+    outs = []
+    for o in (port, emu):
+        o.set_example(ex)
+        g = o.geom_build(tris)
+        acc = np.zeros((W * H, 4), np.float32)
+        rg = o.lookat(*CAM_CB, W, H)
+        for frame in (1, 2):
+            o.path_trace(W, H, frame, g, tris, lights, rg, opt, acc)
+        outs.append(acc)
+        o.geom_free(g)
+    port.set_example(9)
+    assert same(outs[0], outs[1]) and float(outs[0][:, :3].sum()) > 0
+
+
+def test_ao(emu, port):
+    tris = small_scene("blocks_ao")
+    W, H = 96, 54
+    outs = []
+    for o in (port, emu):
+        o.set_example(6)
+        g = o.geom_build(tris)
+        outs.append(o.ao(W, H, g, tris, o.lookat(*CAM_AO, W, H), 16).view(np.uint8).copy())
+        o.geom_free(g)
+    port.set_example(9)
+    assert same(outs[0], outs[1]) and len(np.unique(outs[0])) > 4
+
+
+def test_wide_bvh_equals_brute_force(emu, port):
+    """closest hit (incl. the tie rule) and any-hit of the compressed wide BVH vs the exhaustive loop"""
+    tris = small_scene("blocks_ao")
+    g = emu.geom_build(tris)
+    lib = port.lib
+    lib.orc_closest_hit_brute.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    emu.lib.emu_any_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+    rng = np.random.default_rng(7)
+    hits = 0
+    for i in range(600):
+        o = rng.uniform(-6, 6, 3).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        if i % 5 == 0:
+            d[rng.integers(3)] = 0.0  # axis-parallel component
+        if i % 7 == 0:
+            o = np.round(o)  # origins on grid planes where many block faces lie
+        tmax = 3.402823466e38 if i % 3 else float(rng.uniform(0.5, 8))
+        idx, tuv = emu.closest_hit(g, o, d, 0.0, tmax)
+        tuv2 = np.zeros(3, np.float32)
+        idx2 = lib.orc_closest_hit_brute(tris.ctypes.data, len(tris), o.ctypes.data, d.ctypes.data, 0.0, tmax,
+                                         tuv2.ctypes.data)
+        assert idx == idx2 and (idx < 0 or same(tuv, tuv2)), (i, o, d)
+        assert emu.lib.emu_any_hit(g, o.ctypes.data, d.ctypes.data, 0.0, tmax) == (1 if idx2 >= 0 else 0)
+        hits += idx >= 0
+    assert hits > 100
+    emu.geom_free(g)
+
+
+def test_degenerate_inputs(emu, port):
+    """empty scene, single triangle, 3 triangles (one leaf), duplicated triangles (identical Morton keys)"""
+    W, H = 32, 18
+    cb = small_scene("cornellbox1")
+    for tris in (cb[:0], cb[:1], cb[:3], np.concatenate([cb[:5]] * 4)):
+        tris = np.ascontiguousarray(tris)
+        outs = []
+        for o in (port, emu):
+            g = o.geom_build(tris)
+            outs.append(o.raycast(W, H, g, tris, o.lookat(*CAM_CB, W, H)))
+            o.geom_free(g)
+        assert same(outs[0]["index"], outs[1]["index"]) and same(outs[0]["uv"], outs[1]["uv"])

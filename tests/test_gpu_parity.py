@@ -1,0 +1,334 @@
+"""Parity tests proper: the CUDA kernels, called through the C ABI (libcedecrt.so via ctypes), against the
+CPU oracle (oracle/port, pinned to the reference by test_oracle_pinning.py) on the same seeded inputs.
+
+Bars (north star + tier rules):
+  * index / byte / integer work — primitive ids, uv bits, RGBA8, M — bit-exact.  With CRT_MATH_EXACT the whole
+    ReSTIR chain is bit-exact, stage by stage, because every float op then rounds exactly like the oracle's.
+  * default math (CUDA libdevice float functions, what the reference's NVRTC build computes): accumulated
+    radiance within mean relative L1 <= 1e-3 of the oracle (tolerance from BASELINE.json's north star).
+  * full-size inputs: size-independent properties (BVH == exhaustive search on the GPU, determinism,
+    pixel-class counts, untouched sky/emissive reservoirs).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from helpers import DeviceAsOracle, reservoir_mismatch, same, small_scene
+
+pytestmark = pytest.mark.gpu
+
+CAM_CB = ((0.0, 2.7, 9.0), (0.0, 2.7, 0.0))
+CAM_AO = ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0))
+CAM_RESTIR = ((-0.579885, 22.194597, -6.567105), (5.224952, 20.847435, 1.431192))  # 10_restir_di.cpp:188-189
+REL_L1_TOL = 1e-3  # BASELINE.json north star: "mean relative L1 <= 1e-3"
+
+
+@pytest.fixture(scope="module")
+def rt():
+    import cedecrt
+
+    r = cedecrt.Runtime(0)
+    yield r
+    r.close()
+
+
+@pytest.fixture()
+def dev(rt):
+    import cedecrt
+
+    rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+    return DeviceAsOracle(rt)
+
+
+def lit_blocks_ao():
+    t = small_scene("blocks_ao").copy()
+    t["emissive"][100:140] = (5.0, 4.0, 3.0)
+    return t
+
+
+def staged(name):
+    import stage_assets
+
+    if not stage_assets.have_scene(name):
+        pytest.skip("scene cache assets/%s.tri.xz not staged" % name)
+    return stage_assets.load_scene(name)
+
+
+def rel_l1(a, b):
+    ra, rb = a[:, :3] / a[:, 3:4], b[:, :3] / b[:, 3:4]
+    return float(np.abs(ra - rb).sum() / np.abs(rb).sum())
+
+
+# ------------------------------------------------------------------ traversal
+@pytest.mark.parametrize("scene", ["cornellbox1", "blocks_ao"])
+def test_bvh_equals_exhaustive_search_small(rt, scene):
+    tris = small_scene(scene)
+    d_tris = rt.to_device(tris)
+    g = rt.build_geometry(d_tris)
+    rng = np.random.default_rng(3)
+    n = 20000
+    o = rng.uniform(-7, 7, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[::5, 0] = 0.0
+    d[1::7, 1] = 0.0
+    o[::9] = np.round(o[::9])
+    p1, t1 = rt.trace_closest(g, o, d)
+    p2, t2 = rt.trace_closest(g, o, d, brute=True)
+    assert same(p1, p2) and same(t1, t2)
+    assert (p1 >= 0).sum() > n // 10
+    a1 = rt.trace_any(g, o, d, 0.0, 5.0)
+    p3, _ = rt.trace_closest(g, o, d, 0.0, 5.0, brute=True)
+    assert same(a1, (p3 >= 0).astype(np.int32))
+    g.destroy()
+
+
+def test_bvh_equals_exhaustive_search_blocks_restir(rt):
+    tris = staged("blocks_restir")
+    d_tris = rt.to_device(tris)
+    g = rt.build_geometry(d_tris)
+    st = g.stats()
+    assert st["n_tris"] == 1598368 and st["max_depth"] <= 48
+    rng = np.random.default_rng(5)
+    n = 4096
+    eye = np.array(CAM_RESTIR[0], np.float32)
+    o = (eye + rng.uniform(-20, 20, (n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    p1, t1 = rt.trace_closest(g, o, d)
+    p2, t2 = rt.trace_closest(g, o, d, brute=True)
+    assert same(p1, p2) and same(t1, t2)
+    assert (p1 >= 0).sum() > n // 4
+    g.destroy()
+
+
+@pytest.mark.parametrize("scene,cam,size", [("cornellbox1", CAM_CB, (96, 54)), ("blocks_ao", CAM_AO, (320, 180))])
+def test_raycast_bit_exact(dev, port, scene, cam, size):
+    tris = small_scene(scene)
+    W, H = size
+    outs = []
+    for o in (port, dev):
+        g = o.geom_build(tris)
+        outs.append(o.raycast(W, H, g, tris, o.lookat(*cam, W, H)))
+        o.geom_free(g)
+    assert same(outs[0]["index"], outs[1]["index"]) and same(outs[0]["uv"], outs[1]["uv"])
+    assert (outs[1]["_pad"] == 0).all()
+
+
+def test_raycast_blocks_restir_1080p_pixel_classes(dev, port):
+    """config 4/5 camera on the real scene: bit-exact primitive ids against the oracle on a band of rows, and
+    the pixel-class counts SURVEY.md section 4 extracted from the reference for the whole frame"""
+    tris = staged("blocks_restir")
+    W, H = 1920, 1080
+    g = dev.geom_build(tris)
+    vis = dev.raycast(W, H, g, tris, dev.lookat(*CAM_RESTIR, W, H))
+    idx = vis["index"]
+    em = (tris["emissive"] > 0).any(1)
+    sky = int((idx < 0).sum())
+    emi = int(em[idx[idx >= 0]].sum())
+    assert (sky, emi, W * H - sky - emi) == (197500, 272518, 1603582)
+    gp = port.geom_build(tris)
+    y0, y1 = 500, 564  # 64 rows of the oracle: seconds on a few cores
+    port.set_range(y0 * W, y1 * W)
+    ref = port.raycast(W, H, gp, tris, port.lookat(*CAM_RESTIR, W, H))
+    port.set_range(0, -1)
+    rows = slice((H - y1) * W, (H - y0) * W)  # bottom-up storage
+    assert same(vis["index"][rows], ref["index"][rows]) and same(vis["uv"][rows], ref["uv"][rows])
+    dev.geom_free(g)
+    port.geom_free(gp)
+
+
+# ------------------------------------------------------------------ ReSTIR chain
+@pytest.mark.parametrize("scene", ["cornellbox1", "blocks_ao_lit"])
+def test_restir_chain_bit_exact_in_exact_math_mode(dev, port, scene):
+    import cedecrt
+
+    tris = small_scene("cornellbox1") if scene == "cornellbox1" else lit_blocks_ao()
+    cam, (W, H) = (CAM_CB, (96, 54)) if scene == "cornellbox1" else (CAM_AO, (160, 90))
+    opt = orc.make_options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    port.set_math_mode(1)
+    dev.set_math_mode(cedecrt.MATH_EXACT)
+    chains = []
+    for o in (port, dev):
+        g = o.geom_build(tris)
+        chains.append(orc.RestirChain(o, W, H, tris, g, *cam, opt))
+    for frame in range(3):
+        for ch in chains:
+            ch.step()
+        a, b = chains
+        assert same(a.vis["index"], b.vis["index"]) and same(a.vis["uv"], b.vis["uv"])
+        for name in ("buf0", "buf1", "temporal"):
+            assert reservoir_mismatch(getattr(a, name), getattr(b, name)) == 0, (frame, name)
+        assert same(a.accum, b.accum), frame
+    pa = port.tone_mapping(chains[0].accum, W, H)
+    pb = dev.tone_mapping(chains[1].accum, W, H)
+    assert same(pa, pb)
+    port.set_math_mode(0)
+
+
+def test_restir_options_bit_exact(dev, port):
+    import cedecrt
+
+    tris = small_scene("cornellbox1")
+    W, H = 64, 36
+    port.set_math_mode(1)
+    dev.set_math_mode(cedecrt.MATH_EXACT)
+    for kw in (dict(use_shadowed_target_function=1, use_visibility_reuse=0, use_temporal_resampling=1,
+                    use_spatial_resampling=1, ris_sample_count=8, spatial_resampling_passes=2),
+               dict(use_spatial_resampling=0, use_temporal_resampling=1),
+               dict(use_spatial_resampling=1, use_temporal_resampling=0, spatial_resampling_radius=5.0,
+                    spatial_resampling_sample_count=2, accumulate=1)):
+        opt = orc.make_options(**kw)
+        outs = []
+        for o in (port, dev):
+            g = o.geom_build(tris)
+            ch = orc.RestirChain(o, W, H, tris, g, *CAM_CB, opt)
+            ch.step()
+            ch.step()
+            outs.append((ch.buf0.copy(), ch.buf1.copy(), ch.accum.copy()))
+        assert reservoir_mismatch(outs[0][0], outs[1][0]) == 0 and reservoir_mismatch(outs[0][1], outs[1][1]) == 0
+        assert same(outs[0][2], outs[1][2]), kw
+    port.set_math_mode(0)
+
+
+def test_restir_default_math_within_tolerance(rt, port):
+    """default (libdevice) math: N accumulated frames of the resident frame loop vs the oracle (glibc math)"""
+    import cedecrt
+
+    tris = lit_blocks_ao()
+    W, H, N = 160, 90, 8
+    rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+    app = cedecrt.RestirDI(rt, W, H, tris, *CAM_AO, cedecrt.Options(accumulate=1, use_temporal_resampling=1,
+                                                                   use_spatial_resampling=1))
+    g = port.geom_build(tris)
+    ch = orc.RestirChain(port, W, H, tris, g, *CAM_AO,
+                         orc.make_options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1))
+    for _ in range(N):
+        app.frame()
+        ch.step()
+    acc = app.accumulation.to_host().view(np.float32).reshape(-1, 4)
+    assert same(acc[:, 3], ch.accum[:, 3])
+    err = rel_l1(acc, ch.accum)
+    print("mean relative L1 after %d frames: %.3e" % (N, err))
+    assert err <= REL_L1_TOL
+    # generate_candidate has no transcendental: its output is bit-exact in every math mode
+    vis = app.visibility.to_host()
+    assert same(vis["index"], ch.vis["index"])
+
+
+def test_generate_candidate_bit_exact_on_blocks_restir_band(dev, port):
+    """the 32-candidate RIS loop + visibility-reuse shadow ray on the real 1.6 M-triangle / 146 k-light scene"""
+    tris = staged("blocks_restir")
+    W, H = 1920, 1080
+    lights = orc.light_indices(tris)
+    assert len(lights) == 145982
+    opt = orc.make_options()
+    g, gp = dev.geom_build(tris), port.geom_build(tris)
+    vis = dev.raycast(W, H, g, tris, dev.lookat(*CAM_RESTIR, W, H))
+    res = dev.generate_candidate(W, H, 1, g, tris, vis, CAM_RESTIR[0], lights, opt)
+    y0, y1 = 600, 616
+    port.set_range(y0 * W, y1 * W)
+    ref = np.zeros(W * H, orc.RESERVOIR)
+    port.generate_candidate(W, H, 1, gp, tris, vis, CAM_RESTIR[0], lights, opt, ref)
+    port.set_range(0, -1)
+    rows = slice((H - y1) * W, (H - y0) * W)
+    assert reservoir_mismatch(res[rows], ref[rows]) == 0
+    assert (res[rows]["M"] == 32).sum() > 1000
+
+
+# ------------------------------------------------------------------ examples 06-09
+@pytest.mark.parametrize("ex", [7, 8, 9])
+def test_path_tracers_bit_exact(dev, port, ex):
+    import cedecrt
+
+    tris = small_scene("cornellbox1")
+    W, H = 64, 36
+    opt = orc.make_options(accumulate=1, max_depth=4, ris_sample_count=8, sky_color=(0.1, 0.2, 0.3))
+    lights = orc.light_indices(tris)
+    port.set_math_mode(1)
+    dev.set_math_mode(cedecrt.MATH_EXACT)
+    port.set_example(ex)
+    gp, g = port.geom_build(tris), dev.geom_build(tris)
+    a, b = np.zeros((W * H, 4), np.float32), np.zeros((W * H, 4), np.float32)
+    for frame in (1, 2):
+        port.path_trace(W, H, frame, gp, tris, lights, port.lookat(*CAM_CB, W, H), opt, a)
+        dev.path_trace(ex, W, H, frame, g, tris, lights, dev.lookat(*CAM_CB, W, H), opt, b)
+    port.set_example(9)
+    port.set_math_mode(0)
+    assert same(a, b) and float(a[:, :3].sum()) > 0
+
+
+def test_ao06_bit_exact(dev, port):
+    import cedecrt
+
+    tris = small_scene("blocks_ao")
+    W, H = 160, 90
+    port.set_math_mode(1)
+    dev.set_math_mode(cedecrt.MATH_EXACT)
+    port.set_example(6)
+    gp, g = port.geom_build(tris), dev.geom_build(tris)
+    a = port.ao(W, H, gp, tris, port.lookat(*CAM_AO, W, H), 32)
+    b = dev.ao(W, H, g, tris, dev.lookat(*CAM_AO, W, H), 32)
+    port.set_example(9)
+    port.set_math_mode(0)
+    assert same(a, b)
+
+
+def test_launch_by_name_matches_direct_call(rt):
+    """Shader::launch call shape (crt_launch) == the typed exports"""
+    import ctypes as C
+
+    import cedecrt
+
+    tris = small_scene("cornellbox1")
+    W, H = 64, 36
+    d_tris = rt.to_device(tris)
+    g = rt.build_geometry(d_tris)
+    rg = cedecrt.lookat(*CAM_CB, W, H)
+    v1, v2 = rt.buffer(cedecrt.VISIBILITY, W * H), rt.buffer(cedecrt.VISIBILITY, W * H)
+    rt.raycast(W, H, g, d_tris, rg, v1)
+    rt.launch("raycast", W, H, g, d_tris, rg, v2)
+    assert same(v1.to_host(), v2.to_host())
+    with pytest.raises(cedecrt.CrtError, match="unknown kernel"):
+        rt.launch("no_such_kernel", W)
+    with pytest.raises(cedecrt.CrtError, match="too small"):
+        rt.raycast(W, H, g, d_tris, rg, rt.buffer(cedecrt.VISIBILITY, 10))
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_frame_properties_4k_tiled(rt):
+    """BASELINE config 5 geometry (blocks_restir tiled x6, 3840x2160): determinism, pixel classes, and the
+    reference's untouched-output rule for sky/emissive pixels"""
+    import cedecrt
+    import scenes
+
+    base = staged("blocks_restir")
+    tris = scenes.tile_scene(base, 3, 2, 130.0, 82.0)
+    assert len(tris) == 9590208
+    W, H = 3840, 2160
+    rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+    app = cedecrt.RestirDI(rt, W, H, tris, *CAM_RESTIR, cedecrt.Options(accumulate=1, use_temporal_resampling=1,
+                                                                       use_spatial_resampling=1))
+    assert app.lights.n == 875892
+    app.reservoir1.upload(np.full(app.reservoir1.nbytes, 0xAB, np.uint8))  # sentinel: spatial must not touch sky
+    app.frame()
+    acc1 = app.accumulation.to_host().view(np.float32).reshape(-1, 4)
+    vis = app.visibility.to_host()
+    out1 = app.output.to_host()
+    idx = vis["index"]
+    em = (tris["emissive"] > 0).any(1)
+    sky = idx < 0
+    emi = np.zeros(len(idx), bool)
+    emi[~sky] = em[idx[~sky]]
+    assert 0.05 < sky.mean() < 0.2 and 0.05 < emi.mean() < 0.25
+    assert (acc1[sky, :3] == 0).all() and (acc1[:, 3] == 1).all()
+    assert same(acc1[emi, :3], tris["emissive"][idx[emi]])
+    assert np.isfinite(acc1).all() and float(acc1[~sky & ~emi, :3].mean()) > 0
+    assert (out1.view(np.uint8).reshape(len(out1), -1)[sky | emi] == 0xAB).all()
+    assert (out1["M"][~sky & ~emi] >= 32).all()
+    # determinism: a second app from scratch gives the identical frame
+    app2 = cedecrt.RestirDI(rt, W, H, tris, *CAM_RESTIR, cedecrt.Options(accumulate=1, use_temporal_resampling=1,
+                                                                        use_spatial_resampling=1))
+    app2.frame()
+    assert same(app2.accumulation.to_host(), app.accumulation.to_host())
+    assert same(app2.visibility.to_host()["index"], idx)
