@@ -121,6 +121,7 @@ class SlabRenderer:
         self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
         self.c = cedecrt
         self.rt = cedecrt.Runtime(torch.cuda.current_device())
+        assert torch.cuda.current_stream().cuda_stream != 0, "bench needs a non-default torch stream"
         self.rt.set_stream(torch.cuda.current_stream().cuda_stream)
         self.y0, self.y1 = slab_rows(H, world, rank)
         self.rt.set_row_range(self.y0, self.y1)
@@ -234,6 +235,10 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # a real (non-default) torch stream: kernels, copies, NCCL and the timing events all go to it.  (The legacy
+    # default stream's handle is 0, which crt_set_stream reads as "use the context's own stream".)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tris, cam, workload = load_workload()
