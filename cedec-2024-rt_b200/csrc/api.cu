@@ -1,6 +1,7 @@
 // api.cu — context, memory, timing and the launch-by-name layer of the C ABI (include/cedecrt.h).
 // Replaces the Orochi runtime + common/typedbuffer.hpp + common/shader.hpp of the reference with a thin
 // layer over the CUDA runtime: no HIP/CUDA dual dispatch, no run-time compilation, no CPU fallback.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.cuh"
@@ -46,6 +47,8 @@ extern "C" int crt_init(int device, crt_ctx** out)
     ctx->stream = ctx->own_stream;
     CRT_CUDA(cudaEventCreate(&ctx->ev_start));
     CRT_CUDA(cudaEventCreate(&ctx->ev_stop));
+    if (const char* e = getenv("CRT_WAVEFRONT")) ctx->wavefront = atoi(e);
+    if (const char* e = getenv("CRT_LIGHT_TABLE")) ctx->light_table = atoi(e);
     *out = ctx;
     return CRT_OK;
 }
@@ -57,6 +60,8 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
+    if (ctx->queue_rays) cudaFree(ctx->queue_rays);
+    if (ctx->queue_counters) cudaFree(ctx->queue_counters);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return CRT_OK;

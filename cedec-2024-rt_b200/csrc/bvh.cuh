@@ -18,17 +18,19 @@
 namespace crt
 {
 constexpr int kLeafMaxTris = 3;  // triangles per leaf child (3 x 8 slots = 24 hit-mask bits)
-constexpr int kStackSize = 48;   // >= depth of the wide tree (checked at build time, CRT_ESTACK)
+constexpr int kStackSize = 48;   // >= 2 x depth of the wide tree: one node group + one postponed triangle group
+                                 // per level (checked at build time, CRT_ESTACK)
 
 // 80 bytes, read as five 16-byte words.
 struct alignas(16) WideNode
 {
-    float px, py, pz;            // grid origin (min corner of the node box)
+    float px, py, pz;            // grid origin (one cell below the min corner of the node box)
     uint8_t ex, ey, ez;          // biased exponents: cell size on axis a is 2^(e_a - 127)
     uint8_t imask;               // bit s set: slot s is an inner node
     uint32_t child_base;         // first inner child; child in slot s is child_base + popc(imask & ((1<<s)-1))
     uint32_t tri_base;           // first triangle record of this node's leaf children
-    uint8_t meta[8];             // 0: empty slot; inner: 0xff; leaf: (count << 5) | offset from tri_base
+    uint8_t meta[8];             // 0: empty slot; inner: 0x20 | (24 + slot); leaf: (unary count 1,3,7) << 5 | offset
+                                 // from tri_base — so (meta >> 5) << (meta & 31) is the slot's hit-mask contribution
     uint8_t qlo[3][8];           // per axis, per slot: box min in grid cells (rounded down)
     uint8_t qhi[3][8];           // box max in grid cells (rounded up)
 };
@@ -48,6 +50,7 @@ struct Bvh
 {
     const WideNode* nodes;
     const WideTri* tris;
+    float postpone_ratio;  // triangle-postponing threshold of the walk (0 = never postpone), see walk_step
 };
 
 struct Hit
@@ -91,14 +94,228 @@ CRT_HD u4 load_u4(const void* p)
 #endif
 }
 
-// byte k of a 32-bit word as float.  Device: PRMT builds the bits of 2^23 + byte, one FADD removes 2^23.
-CRT_HD float byte_to_float(uint32_t w, int k)
+// Quantised plane coordinate q (byte k of a word) as the float 1 + q * 2^-15: on the device a single PRMT drops
+// the byte into mantissa bits 8..15 of 1.0f — no integer-to-float conversion and no bias subtraction.
+// intersect_node folds the "1 +" and the 2^-15 into the per-node constants.
+CRT_HD float byte_to_unit_float(uint32_t w, int k)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 | k)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x3f800000u, 0x7604 | (k << 4)));
 #else
-    return (float)((w >> (8 * k)) & 0xffu);
+    return u2f(0x3f800000u | (((w >> (8 * k)) & 0xffu) << 8));
 #endif
+}
+// The folded form rounds (o - a * 2^15) once, an error of at most cell/512 in space; child boxes are therefore
+// quantised with a margin of kQuantMargin cells on every side (bvh_build.cuh: collapse_item), which keeps the
+// slab test conservative by construction.
+constexpr float kQuantMargin = 1.0f / 128.0f;
+
+// test-only instrumentation (tests/emu with -DCRT_COUNT): per-thread node / triangle step counters
+#if defined(CRT_COUNT) && !defined(__CUDA_ARCH__)
+extern thread_local unsigned long long g_count_nodes, g_count_tris;
+#define CRT_COUNT_NODE() (++g_count_nodes)
+#define CRT_COUNT_TRI() (++g_count_tris)
+#else
+#define CRT_COUNT_NODE() ((void)0)
+#define CRT_COUNT_TRI() ((void)0)
+#endif
+
+// ---- traversal building blocks (shared by the per-thread walk below and the persistent-warp kernels)
+struct RaySetup
+{
+    f3 ro, rd;
+    float idx, idy, idz;  // reciprocal direction
+    uint32_t octinv;      // 7 ^ octant: `slot ^ octinv` is the front-to-back priority of a child slot
+    bool nx, ny, nz;
+};
+CRT_HD RaySetup setup_ray(f3 ro, f3 rd)
+{
+    RaySetup r;
+    r.ro = ro;
+    r.rd = rd;
+    // an exactly axis-parallel component becomes +-1e-20 so that the slab arithmetic never sees 0 * inf
+    // (the padded boxes make the perturbation harmless)
+    const float dx = fabsf(rd.x) > 1e-20f ? rd.x : copysignf(1e-20f, rd.x);
+    const float dy = fabsf(rd.y) > 1e-20f ? rd.y : copysignf(1e-20f, rd.y);
+    const float dz = fabsf(rd.z) > 1e-20f ? rd.z : copysignf(1e-20f, rd.z);
+    r.idx = 1.0f / dx;
+    r.idy = 1.0f / dy;
+    r.idz = 1.0f / dz;
+    r.nx = dx < 0.0f;
+    r.ny = dy < 0.0f;
+    r.nz = dz < 0.0f;
+    r.octinv = 7u ^ ((r.nx ? 1u : 0u) | (r.ny ? 2u : 0u) | (r.nz ? 4u : 0u));
+    return r;
+}
+
+// Intersect the eight child boxes of one node with the ray segment [tmin, tmax].
+// Returns the hit mask: bits 24..31 inner children by priority, bits 0..23 triangles of hit leaf children.
+CRT_HD uint32_t intersect_node(const Bvh& bvh, uint32_t node_idx, const RaySetup& r, float tmin, float tmax,
+                               uint32_t& child_base, uint32_t& tri_base, uint32_t& imask_out)
+{
+    CRT_COUNT_NODE();
+    const char* np = (const char*)(bvh.nodes + node_idx);
+    const u4 n0 = load_u4(np), n1 = load_u4(np + 16), n2 = load_u4(np + 32), n3 = load_u4(np + 48),
+             n4 = load_u4(np + 64);
+    const uint32_t e_imask = n0.w;
+    const float sx = u2f((e_imask & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23),
+                sz = u2f(((e_imask >> 16) & 0xffu) << 23);
+    const uint32_t imask = e_imask >> 24;
+    // plane at q cells: t = (p + q*cell - ro) / d = q * a + o with a = cell/d, o = (p - ro)/d.  With the byte
+    // read as u = 1 + q * 2^-15:  t = u * (a * 2^15) + (o - a * 2^15)
+    const float ax = sx * r.idx * 32768.0f, ay = sy * r.idy * 32768.0f, az = sz * r.idz * 32768.0f;  // exact scalings
+    const float ox = (u2f(n0.x) - r.ro.x) * r.idx - ax, oy = (u2f(n0.y) - r.ro.y) * r.idy - ay,
+                oz = (u2f(n0.z) - r.ro.z) * r.idz - az;
+    // word layout: n2 = qlo.x[0..3] qlo.x[4..7] qlo.y[0..3] qlo.y[4..7]; n3 = qlo.z.. qhi.x..; n4 = qhi.y.. qhi.z..
+    const uint32_t nearx[2] = {r.nx ? n3.z : n2.x, r.nx ? n3.w : n2.y}, farx[2] = {r.nx ? n2.x : n3.z, r.nx ? n2.y : n3.w};
+    const uint32_t neary[2] = {r.ny ? n4.x : n2.z, r.ny ? n4.y : n2.w}, fary[2] = {r.ny ? n2.z : n4.x, r.ny ? n2.w : n4.y};
+    const uint32_t nearz[2] = {r.nz ? n4.z : n3.x, r.nz ? n4.w : n3.y}, farz[2] = {r.nz ? n3.x : n4.z, r.nz ? n3.y : n4.w};
+    // per-slot hit-mask contribution, four slots per word (Ylitie et al. 2017, listing 2): inner children carry
+    // 24 + slot in the low five meta bits, which `^ octinv` turns into the front-to-back priority
+    const uint32_t octinv4 = r.octinv * 0x01010101u;
+    uint32_t bit_index[2], child_bits[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++)
+    {
+        const uint32_t meta4 = w ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;  // bits 3 and 4 both set: index >= 24
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;            // 0xff in every inner slot's byte
+        bit_index[w] = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        child_bits[w] = (meta4 >> 5) & 0x07070707u;
+    }
+    uint32_t hits = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+    {
+        const int w = s >> 2, k = s & 3;
+        const float t0 = fmaxf(fmaxf(fmaf(byte_to_unit_float(nearx[w], k), ax, ox), fmaf(byte_to_unit_float(neary[w], k), ay, oy)),
+                               fmaxf(fmaf(byte_to_unit_float(nearz[w], k), az, oz), tmin));
+        const float t1 = fminf(fminf(fmaf(byte_to_unit_float(farx[w], k), ax, ox), fmaf(byte_to_unit_float(fary[w], k), ay, oy)),
+                               fminf(fmaf(byte_to_unit_float(farz[w], k), az, oz), tmax));
+        const uint32_t bits = ((child_bits[w] >> (8 * k)) & 0xffu) << ((bit_index[w] >> (8 * k)) & 0xffu);
+        hits |= t0 <= t1 ? bits : 0u;  // an empty slot has meta 0, hence bits 0
+    }
+    child_base = n1.x;
+    tri_base = n1.y;
+    imask_out = imask;
+    return hits;
+}
+
+// One triangle record against the ray: the reference test, then the tie rule (smaller t, then larger id).
+CRT_HD bool intersect_wide_tri(const WideTri* tp, const RaySetup& r, float tmin, Hit& hit)
+{
+    CRT_COUNT_TRI();
+    const char* q = (const char*)tp;
+    const u4 a = load_u4(q), b = load_u4(q + 16), c = load_u4(q + 32);
+    float t, u, v;
+    if (!ray_triangle(r.ro, r.rd, tmin, hit.t, f3{u2f(a.x), u2f(a.y), u2f(a.z)}, f3{u2f(b.x), u2f(b.y), u2f(b.z)},
+                      f3{u2f(c.x), u2f(c.y), u2f(c.z)}, t, u, v))
+        return false;
+    const int prim = (int)a.w;
+    if (!(t < hit.t || hit.prim < 0 || prim > hit.prim)) return false;
+    hit.t = t;
+    hit.u = u;
+    hit.v = v;
+    hit.prim = prim;
+    return true;
+}
+
+// ---- the walk as a resumable state machine (one call of walk_step = one outer iteration)
+//
+// Divergence control, after Ylitie et al. 2017 ("Efficient Incoherent Ray Traversal on GPUs Through
+// Compressed Wide BVHs"): a lane that owns triangles while fewer than kPostponeRatio of the warp's walking
+// lanes are in the triangle loop pushes its triangle group on the stack and goes on with node steps, so
+// the ~100-instruction triangle test and the ~300-instruction node step each run with many lanes instead
+// of every lane waiting for the slowest one in every phase.  Any visiting order gives the same result:
+// the closest hit is decided by (t, primitive id) alone.
+constexpr float kPostponeRatio = 0.25f;  // default of Bvh::postpone_ratio (CRT_POSTPONE overrides)
+
+#if defined(__CUDA_ARCH__)
+#define CRT_LANES_HERE() __popc(__activemask())
+#define CRT_LANES_WALKING() __popc(__activemask())
+#else
+// host build (tests/emu): 0 = never postpone, 1 = postpone whenever allowed (exercises that path)
+extern int g_emu_postpone;
+#define CRT_LANES_HERE() (g_emu_postpone ? 0 : 32)
+#define CRT_LANES_WALKING() 32
+#endif
+
+struct Walk
+{
+    uint32_t stack_base[kStackSize], stack_mask[kStackSize];
+    int sp;
+    uint32_t ng_base, ng_mask;  // node group: inner-child hits in bits 24..31 (by priority), imask in bits 0..7
+    uint32_t tri_base, tmask;   // triangle group: hit triangles of the last node's leaf children
+};
+CRT_HD void walk_begin(Walk& w, const RaySetup& r)
+{
+    w.sp = 0;
+    // the root as the only child (slot 0) of a virtual group at base 0
+    w.ng_base = 0;
+    w.ng_mask = 1u << (24 + (0u ^ r.octinv));
+    w.tri_base = 0;
+    w.tmask = 0;
+}
+enum { kWalkContinue = 0, kWalkDone = 1, kWalkHitAny = 2 };
+
+// lanes_walking: number of lanes of the warp that entered this iteration (read at a converged point)
+template <bool ANY, bool POSTPONE>
+CRT_HD int walk_step(const Bvh& bvh, Walk& w, const RaySetup& r, float tmin, Hit& hit, int lanes_walking)
+{
+    // ---- node work: at most one node step
+    if (w.tmask == 0)
+    {
+        if ((w.ng_mask >> 24) == 0)
+        {
+            if (w.sp == 0) return kWalkDone;
+            --w.sp;
+            const uint32_t b = w.stack_base[w.sp], m = w.stack_mask[w.sp];
+            if (m >> 24)
+            {
+                w.ng_base = b;
+                w.ng_mask = m;
+            }
+            else  // a postponed triangle group
+            {
+                w.tri_base = b;
+                w.tmask = m;
+            }
+        }
+        if (w.tmask == 0)
+        {
+            const int bit = 31 - clz32(w.ng_mask);  // bits 24..31 are non-empty here
+            w.ng_mask &= ~(1u << bit);
+            const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+            const uint32_t node_idx = w.ng_base + (uint32_t)popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
+            if (w.ng_mask >> 24)
+            {
+                w.stack_base[w.sp] = w.ng_base;
+                w.stack_mask[w.sp] = w.ng_mask;
+                ++w.sp;
+            }
+            uint32_t imask;
+            const uint32_t hits = intersect_node(bvh, node_idx, r, tmin, hit.t, w.ng_base, w.tri_base, imask);
+            w.ng_mask = (hits & 0xff000000u) | imask;
+            w.tmask = hits & 0x00ffffffu;
+        }
+    }
+    // ---- triangle work
+    const WideTri* tp = bvh.tris + w.tri_base;
+    while (w.tmask)
+    {
+        if (POSTPONE && (w.ng_mask >> 24) != 0 && (float)CRT_LANES_HERE() < bvh.postpone_ratio * (float)lanes_walking)
+        {
+            w.stack_base[w.sp] = w.tri_base;
+            w.stack_mask[w.sp] = w.tmask;
+            ++w.sp;
+            w.tmask = 0;
+            break;
+        }
+        const int i = 31 - clz32(w.tmask & (0u - w.tmask));
+        w.tmask &= w.tmask - 1u;
+        if (intersect_wide_tri(tp + i, r, tmin, hit) && ANY) return kWalkHitAny;
+    }
+    return kWalkContinue;
 }
 
 // Closest hit (ANY = false) in [tmin, tmax]: smallest t, ties -> larger primitive id.
@@ -109,100 +326,14 @@ CRT_HD bool trace(const Bvh& bvh, f3 ro, f3 rd, float tmin, float tmax, Hit& hit
     hit.prim = -1;
     hit.t = tmax;
     hit.u = hit.v = 0.0f;
-
-    // reciprocal direction; an exactly axis-parallel component becomes +-1e-20 so that the slab
-    // arithmetic never sees 0 * inf (the padded boxes make the perturbation harmless)
-    const float dx = fabsf(rd.x) > 1e-20f ? rd.x : copysignf(1e-20f, rd.x);
-    const float dy = fabsf(rd.y) > 1e-20f ? rd.y : copysignf(1e-20f, rd.y);
-    const float dz = fabsf(rd.z) > 1e-20f ? rd.z : copysignf(1e-20f, rd.z);
-    const float idx = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
-    const bool nx = dx < 0.0f, ny = dy < 0.0f, nz = dz < 0.0f;
-    const uint32_t octinv = 7u ^ ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
-
-    uint32_t stack_base[kStackSize], stack_mask[kStackSize];
-    int sp = 0;
-    uint32_t node_idx = 0;
-    uint32_t ng_base = 0, ng_mask = 0;  // current node group: inner-child hits in bits 24..31, imask in bits 0..7
-
+    const RaySetup r = setup_ray(ro, rd);
+    Walk w;
+    walk_begin(w, r);
     for (;;)
     {
-        // ---- intersect the eight child boxes of node_idx
-        const char* np = (const char*)(bvh.nodes + node_idx);
-        const u4 n0 = load_u4(np), n1 = load_u4(np + 16), n2 = load_u4(np + 32), n3 = load_u4(np + 48),
-                 n4 = load_u4(np + 64);
-        const uint32_t e_imask = n0.w;
-        const float sx = u2f((e_imask & 0xffu) << 23), sy = u2f(((e_imask >> 8) & 0xffu) << 23),
-                    sz = u2f(((e_imask >> 16) & 0xffu) << 23);
-        const uint32_t imask = e_imask >> 24;
-        const float ax = sx * idx, ay = sy * idy, az = sz * idz;  // exact power-of-two scaling
-        const float ox = (u2f(n0.x) - ro.x) * idx, oy = (u2f(n0.y) - ro.y) * idy, oz = (u2f(n0.z) - ro.z) * idz;
-        // word layout: n2 = qlo.x[0..3] qlo.x[4..7] qlo.y[0..3] qlo.y[4..7]; n3 = qlo.z.. qhi.x..; n4 = qhi.y.. qhi.z..
-        const uint32_t lox[2] = {n2.x, n2.y}, loy[2] = {n2.z, n2.w}, loz[2] = {n3.x, n3.y};
-        const uint32_t hix[2] = {n3.z, n3.w}, hiy[2] = {n4.x, n4.y}, hiz[2] = {n4.z, n4.w};
-        const uint32_t meta[2] = {n1.z, n1.w};
-        uint32_t hits = 0;
-#pragma unroll
-        for (int s = 0; s < 8; s++)
-        {
-            const int w = s >> 2, k = s & 3;
-            const uint32_t m = (meta[w] >> (8 * k)) & 0xffu;
-            const float nearx = byte_to_float(nx ? hix[w] : lox[w], k), farx = byte_to_float(nx ? lox[w] : hix[w], k);
-            const float neary = byte_to_float(ny ? hiy[w] : loy[w], k), fary = byte_to_float(ny ? loy[w] : hiy[w], k);
-            const float nearz = byte_to_float(nz ? hiz[w] : loz[w], k), farz = byte_to_float(nz ? loz[w] : hiz[w], k);
-            const float t0 = fmaxf(fmaxf(fmaf(nearx, ax, ox), fmaf(neary, ay, oy)), fmaxf(fmaf(nearz, az, oz), tmin));
-            const float t1 = fminf(fminf(fmaf(farx, ax, ox), fmaf(fary, ay, oy)), fminf(fmaf(farz, az, oz), hit.t));
-            if (m != 0 && t0 <= t1)
-            {
-                if ((imask >> s) & 1u) hits |= 1u << (24 + (s ^ octinv));
-                else hits |= ((1u << (m >> 5)) - 1u) << (m & 31u);
-            }
-        }
-        ng_base = n1.x;
-        ng_mask = (hits & 0xff000000u) | imask;
-        uint32_t tmask = hits & 0x00ffffffu;
-
-        // ---- triangles of this node's leaf children that survived the box test
-        const WideTri* tp = bvh.tris + n1.y;
-        while (tmask)
-        {
-            const int i = 31 - clz32(tmask & (0u - tmask));
-            tmask &= tmask - 1u;
-            const char* q = (const char*)(tp + i);
-            const u4 a = load_u4(q), b = load_u4(q + 16), c = load_u4(q + 32);
-            float t, u, v;
-            if (ray_triangle(ro, rd, tmin, hit.t, f3{u2f(a.x), u2f(a.y), u2f(a.z)}, f3{u2f(b.x), u2f(b.y), u2f(b.z)},
-                             f3{u2f(c.x), u2f(c.y), u2f(c.z)}, t, u, v))
-            {
-                const int prim = (int)a.w;
-                if (t < hit.t || hit.prim < 0 || prim > hit.prim)
-                {
-                    hit.t = t;
-                    hit.u = u;
-                    hit.v = v;
-                    hit.prim = prim;
-                    if (ANY) return true;
-                }
-            }
-        }
-
-        // ---- next node: nearest remaining child of the current group, else pop
-        if ((ng_mask >> 24) == 0)
-        {
-            if (sp == 0) break;
-            --sp;
-            ng_base = stack_base[sp];
-            ng_mask = stack_mask[sp];
-        }
-        const int bit = 31 - clz32(ng_mask);  // bits 24..31 are non-empty here
-        ng_mask &= ~(1u << bit);
-        const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
-        node_idx = ng_base + (uint32_t)popc(ng_mask & 0xffu & ((1u << slot) - 1u));
-        if (ng_mask >> 24)
-        {
-            stack_base[sp] = ng_base;
-            stack_mask[sp] = ng_mask;
-            ++sp;
-        }
+        const int lanes = CRT_LANES_WALKING();
+        const int st = walk_step<ANY, true>(bvh, w, r, tmin, hit, lanes);
+        if (st != kWalkContinue) break;
     }
     return hit.prim >= 0;
 }

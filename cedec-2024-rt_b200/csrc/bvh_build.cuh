@@ -4,9 +4,11 @@
 //   1 tri_bounds      triangle AABB + scene bounds (atomic min/max)
 //   2 morton_key      63-bit Morton code of the centroid            -> radix sort (cub)
 //   3 lbvh_node       Karras 2012 binary radix tree, one inner node per thread
-//   4 lbvh_refit      bottom-up boxes and triangle counts, second arrival at a node continues
-//   5 collapse_item   top-down, level by level: open the largest-area child until a node has 8 children,
-//                     subtrees of <= 3 triangles become leaf children; children are matched to octant
+//   4 lbvh_refit      bottom-up boxes (second arrival at a node continues) and, in the same sweep, the
+//                     SAH-optimal way to cut every subtree into at most i = 1..7 wide-BVH children
+//                     (dynamic programme of Ylitie et al. 2017, section 3.1)
+//   5 collapse_item   top-down, level by level: a wide node takes the <= 8 children the programme chose;
+//                     subtrees of <= 3 triangles may become leaf children; children are matched to octant
 //                     slots, boxes are quantised outward to the node's 8-bit grid, triangles are written
 //                     as 48-byte records next to each other
 //
@@ -123,7 +125,78 @@ struct BinTree
     uint32_t* count;    // [n-1]  triangles under inner node
     float* box;         // [2n-1][6]  padded AABB
     uint32_t* visits;   // [n-1]  refit arrival counters (zeroed)
+    float* cost;        // [2n-1][7]  c(node, i): least SAH cost of the subtree as a forest of <= i wide-BVH children
+    uint8_t* split;     // [2n-1][8]  [0]: 1 = c(node,1) is a leaf; [j-1], j = 2..8: triangles... see sah_plan_node
 };
+
+// SAH constants: one node step (8 child boxes) vs one triangle test, as in Ylitie et al. 2017
+constexpr float kCostNode = 1.0f, kCostTri = 0.3f, kCostInf = 1.0e30f;
+
+// c(n,1) = min(leaf, internal);  internal = distribute(n,8) + area * kCostNode
+// c(n,i) = min(distribute(n,i), c(n,i-1)), i = 2..7;  distribute(n,j) = min_k c(left,k) + c(right,j-k)
+// split[j-1] (j = 2..8) = the k of the best distribution, or 0 when c(n,j) = c(n,j-1) ("use fewer roots")
+CRT_HD void sah_plan_leaf(const BinTree& bt, uint32_t id, float half_area)
+{
+    float* c = bt.cost + (size_t)id * 7;
+    uint8_t* sp = bt.split + (size_t)id * 8;
+    for (int i = 0; i < 7; i++) c[i] = half_area * kCostTri;
+    sp[0] = 1;
+    for (int j = 1; j < 8; j++) sp[j] = 0;
+}
+CRT_HD void sah_plan_node(const BinTree& bt, uint32_t id, uint32_t l, uint32_t r, float half_area, uint32_t tri_count)
+{
+    float cl[8], cr[8];
+    for (int i = 1; i <= 7; i++)
+    {
+#if defined(__CUDA_ARCH__)
+        // a child's table may have been written by another thread: read it through L2
+        cl[i] = __ldcg(bt.cost + (size_t)l * 7 + i - 1);
+        cr[i] = __ldcg(bt.cost + (size_t)r * 7 + i - 1);
+#else
+        cl[i] = bt.cost[(size_t)l * 7 + i - 1];
+        cr[i] = bt.cost[(size_t)r * 7 + i - 1];
+#endif
+    }
+    float dist[9];
+    uint8_t arg[9];
+    for (int j = 2; j <= 8; j++)
+    {
+        float best = kCostInf * 4.0f;
+        int bk = 1;
+        for (int k = 1; k < j; k++)
+        {
+            if (k > 7 || j - k > 7) continue;
+            const float v = cl[k] + cr[j - k];
+            if (v < best)
+            {
+                best = v;
+                bk = k;
+            }
+        }
+        dist[j] = best;
+        arg[j] = (uint8_t)bk;
+    }
+    float* c = bt.cost + (size_t)id * 7;
+    uint8_t* sp = bt.split + (size_t)id * 8;
+    const float c_internal = dist[8] + half_area * kCostNode;
+    const float c_leaf = tri_count <= (uint32_t)kLeafMaxTris ? half_area * (float)tri_count * kCostTri : kCostInf;
+    c[0] = c_leaf <= c_internal ? c_leaf : c_internal;
+    sp[0] = c_leaf <= c_internal ? 1 : 0;
+    sp[7] = arg[8];
+    for (int i = 2; i <= 7; i++)
+    {
+        if (dist[i] < c[i - 2])
+        {
+            c[i - 1] = dist[i];
+            sp[i - 1] = arg[i];
+        }
+        else
+        {
+            c[i - 1] = c[i - 2];
+            sp[i - 1] = 0;
+        }
+    }
+}
 
 CRT_HD int lbvh_delta(const uint64_t* keys, uint32_t n, int i, int j)
 {
@@ -184,6 +257,7 @@ CRT_HD void lbvh_refit(uint32_t leaf, const float* tris60, const uint32_t* sorte
     b.hi = b.hi + f3{pad, pad, pad};
     uint32_t id = (bt.n - 1) + leaf;
     store_box(bt.box, id, b);
+    sah_plan_leaf(bt, id, aabb_half_area(b));
     if (bt.n == 1) return;
     uint32_t p = bt.parent[id];
     while (p != 0xffffffffu)
@@ -205,6 +279,7 @@ CRT_HD void lbvh_refit(uint32_t leaf, const float* tris60, const uint32_t* sorte
         b = aabb_union(load_box(bt.box, bt.left[p]), load_box(bt.box, bt.right[p]));
 #endif
         store_box(bt.box, p, b);
+        sah_plan_node(bt, p, bt.left[p], bt.right[p], aabb_half_area(b), bt.count[p]);
         p = bt.parent[p];
     }
 }
@@ -230,47 +305,58 @@ CRT_HD uint32_t bin_first(const BinTree& bt, uint32_t id) { return id >= bt.n - 
 
 CRT_HD uint8_t quant_exponent(float extent)
 {
-    // smallest e with extent / 2^e <= 255, as a biased exponent; extent >= 0
+    // smallest e with extent / 2^e <= 250, as a biased exponent; extent >= 0.  The grid starts one cell below
+    // the node box and child boxes get kQuantMargin cells of slack, so 250 cells of extent use q = 0..252.
     if (!(extent > 0.0f)) return 1;
-    int e = (int)((f2u(extent) >> 23) & 0xffu) - 127 - 7;  // 2^e ~ extent / 128 .. extent / 256
+    int e = (int)((f2u(extent) >> 23) & 0xffu) - 127 - 8;  // 2^e ~ extent / 256 .. extent / 512
     if (e < -126) e = -126;
-    while (extent / u2f((uint32_t)(e + 127) << 23) > 255.0f) ++e;
+    while (extent / u2f((uint32_t)(e + 127) << 23) > 250.0f) ++e;
     return (uint8_t)(e + 127);
 }
 
 CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint32_t* sorted_idx, const BinTree& bt,
                           const WideOut& out)
 {
+    // the <= 8 children the SAH plan chose for this subtree (sah_plan_node): walk the recorded splits
     uint32_t ch[8];
-    int cnt;
-    if (bin_tri_count(bt, it.bnode) <= (uint32_t)kLeafMaxTris)
+    bool ch_leaf[8];
+    int cnt = 0;
+    if (bt.split[(size_t)it.bnode * 8] == 1)
     {
-        ch[0] = it.bnode;  // whole tree is one leaf (n <= 3)
+        ch[0] = it.bnode;  // the whole tree is one leaf (n <= 3)
+        ch_leaf[0] = true;
         cnt = 1;
     }
     else
     {
-        ch[0] = bt.left[it.bnode];
-        ch[1] = bt.right[it.bnode];
-        cnt = 2;
-        while (cnt < 8)
+        uint32_t st_node[16];
+        int st_j[16], sp = 0;
+        const int k8 = bt.split[(size_t)it.bnode * 8 + 7];
+        st_node[sp] = bt.right[it.bnode];
+        st_j[sp++] = 8 - k8;
+        st_node[sp] = bt.left[it.bnode];
+        st_j[sp++] = k8;
+        while (sp)
         {
-            int best = -1;
-            float best_area = -1.0f;
-            for (int k = 0; k < cnt; k++)
+            --sp;
+            const uint32_t m = st_node[sp];
+            int j = st_j[sp];
+            const uint8_t* ms = bt.split + (size_t)m * 8;
+            while (j > 1 && ms[j - 1] == 0) --j;  // c(m,j) = c(m,j-1): fewer roots are at least as good
+            if (j == 1)
             {
-                if (bin_tri_count(bt, ch[k]) <= (uint32_t)kLeafMaxTris) continue;
-                const float a = aabb_half_area(load_box(bt.box, ch[k]));
-                if (a > best_area)
-                {
-                    best_area = a;
-                    best = k;
-                }
+                ch[cnt] = m;
+                ch_leaf[cnt] = ms[0] == 1;
+                ++cnt;
             }
-            if (best < 0) break;
-            const uint32_t c = ch[best];
-            ch[best] = bt.left[c];
-            ch[cnt++] = bt.right[c];
+            else
+            {
+                const int k = ms[j - 1];
+                st_node[sp] = bt.right[m];
+                st_j[sp++] = j - k;
+                st_node[sp] = bt.left[m];
+                st_j[sp++] = k;
+            }
         }
     }
 
@@ -322,14 +408,15 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
     for (int k = 0; k < cnt; k++) child_in_slot[slot_of[k]] = k;
 
     WideNode wn;
-    wn.px = nb.lo.x;
-    wn.py = nb.lo.y;
-    wn.pz = nb.lo.z;
     wn.ex = quant_exponent(nb.hi.x - nb.lo.x);
     wn.ey = quant_exponent(nb.hi.y - nb.lo.y);
     wn.ez = quant_exponent(nb.hi.z - nb.lo.z);
-    const float inv_cell[3] = {1.0f / u2f((uint32_t)wn.ex << 23), 1.0f / u2f((uint32_t)wn.ey << 23),
-                               1.0f / u2f((uint32_t)wn.ez << 23)};
+    const float cell[3] = {u2f((uint32_t)wn.ex << 23), u2f((uint32_t)wn.ey << 23), u2f((uint32_t)wn.ez << 23)};
+    const float inv_cell[3] = {1.0f / cell[0], 1.0f / cell[1], 1.0f / cell[2]};
+    // grid origin one cell below the box, so that the lower margin never needs clamping
+    wn.px = nb.lo.x - cell[0];
+    wn.py = nb.lo.y - cell[1];
+    wn.pz = nb.lo.z - cell[2];
 
     uint32_t n_inner = 0, n_leaf_tris = 0;
     uint8_t imask = 0;
@@ -337,13 +424,12 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
     {
         const int k = child_in_slot[s];
         if (k < 0) continue;
-        const uint32_t tc = bin_tri_count(bt, ch[k]);
-        if (tc > (uint32_t)kLeafMaxTris)
+        if (!ch_leaf[k])
         {
             imask |= (uint8_t)(1u << s);
             n_inner++;
         }
-        else n_leaf_tris += tc;
+        else n_leaf_tris += bin_tri_count(bt, ch[k]);
     }
     const uint32_t child_base = n_inner ? CRT_ATOMIC_ADD(out.node_count, n_inner) : 0u;
     const uint32_t tri_base = n_leaf_tris ? CRT_ATOMIC_ADD(out.tri_count, n_leaf_tris) : 0u;
@@ -353,7 +439,7 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
     wn.tri_base = tri_base;
 
     uint32_t inner_rank = 0, tri_off = 0;
-    const float nlo[3] = {nb.lo.x, nb.lo.y, nb.lo.z};
+    const float nlo[3] = {wn.px, wn.py, wn.pz};
     for (int s = 0; s < 8; s++)
     {
         const int k = child_in_slot[s];
@@ -370,21 +456,22 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
         const float clo[3] = {cb[k].lo.x, cb[k].lo.y, cb[k].lo.z}, chi[3] = {cb[k].hi.x, cb[k].hi.y, cb[k].hi.z};
         for (int a = 0; a < 3; a++)
         {
-            const float ql = floorf((clo[a] - nlo[a]) * inv_cell[a]);
-            const float qh = ceilf((chi[a] - nlo[a]) * inv_cell[a]);
+            // outward rounding plus kQuantMargin cells of slack (see bvh.cuh: byte_to_unit_float)
+            const float ql = floorf((clo[a] - nlo[a]) * inv_cell[a] - kQuantMargin);
+            const float qh = ceilf((chi[a] - nlo[a]) * inv_cell[a] + kQuantMargin);
             wn.qlo[a][s] = (uint8_t)fminf(fmaxf(ql, 0.0f), 255.0f);
             wn.qhi[a][s] = (uint8_t)fminf(fmaxf(qh, 0.0f), 255.0f);
         }
         const uint32_t tc = bin_tri_count(bt, ch[k]);
-        if (tc > (uint32_t)kLeafMaxTris)
+        if (!ch_leaf[k])
         {
-            wn.meta[s] = 0xff;
+            wn.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
             out.next[next_base + inner_rank] = CollapseItem{ch[k], child_base + inner_rank};
             inner_rank++;
         }
         else
         {
-            wn.meta[s] = (uint8_t)((tc << 5) | tri_off);
+            wn.meta[s] = (uint8_t)((((1u << tc) - 1u) << 5) | tri_off);  // unary count
             const uint32_t f = bin_first(bt, ch[k]);
             for (uint32_t j = 0; j < tc; j++)
             {

@@ -17,6 +17,12 @@ struct crt_ctx
     int math_mode = CRT_MATH_LIBDEVICE;
     int sm_count = 0;
     char name[256] = {0};
+    // wavefront shadow rays (shadow_queue.cuh): ray queue + {count, next} counters, grown on demand
+    void* queue_rays = nullptr;
+    unsigned* queue_counters = nullptr;
+    size_t queue_capacity = 0;
+    int wavefront = 1;  // 0: trace shadow rays inside the per-pixel kernels (CRT_WAVEFRONT=0)
+    int light_table = 1;  // 0: sample lights through lights[] -> triangles[] like the reference (CRT_LIGHT_TABLE=0)
     int row_begin = 0, row_end = -1;  // rows of yi this context computes (crt_set_row_range); -1 = image height
     unsigned long long launches = 0;  // kernels launched through this context (bench.py: gpu_launches)
 };
@@ -31,7 +37,12 @@ struct crt_geometry_t
     float build_ms = 0.0f;
     float pad = 0.0f;
     int device = 0;
-    crt::Bvh view() const { return crt::Bvh{nodes, tris}; }
+    // 64-byte light records (restir_core.cuh: LightRec) for the light list last seen by generate_candidate
+    void* light_table = nullptr;
+    const void* light_table_key = nullptr;
+    size_t light_table_n = 0;
+    float postpone_ratio = crt::kPostponeRatio;
+    crt::Bvh view() const { return crt::Bvh{nodes, tris, postpone_ratio}; }
 };
 
 namespace crt

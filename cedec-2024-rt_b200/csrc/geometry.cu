@@ -84,6 +84,7 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
     g->src = d_tris;
     g->n_tris = n;
     g->device = ctx->device;
+    if (const char* e = getenv("CRT_POSTPONE")) g->postpone_ratio = (float)atof(e);
 
     if (n == 0)
     {
@@ -150,7 +151,7 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
 
     // ---- 3/4: binary radix tree + bottom-up boxes
     const uint32_t n_inner = n - 1;
-    DevMem m_left, m_right, m_parent, m_first, m_count, m_box, m_visits;
+    DevMem m_left, m_right, m_parent, m_first, m_count, m_box, m_visits, m_cost, m_split;
     CRT_ALLOC(m_left, n_inner * sizeof(uint32_t));
     CRT_ALLOC(m_right, n_inner * sizeof(uint32_t));
     CRT_ALLOC(m_parent, (2 * (size_t)n - 1) * sizeof(uint32_t));
@@ -158,6 +159,8 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
     CRT_ALLOC(m_count, n_inner * sizeof(uint32_t));
     CRT_ALLOC(m_box, (2 * (size_t)n - 1) * 6 * sizeof(float));
     CRT_ALLOC(m_visits, n_inner * sizeof(uint32_t));
+    CRT_ALLOC(m_cost, (2 * (size_t)n - 1) * 7 * sizeof(float));
+    CRT_ALLOC(m_split, (2 * (size_t)n - 1) * 8);
     CRT_CUDA(cudaMemsetAsync(m_visits.p, 0, n_inner ? n_inner * sizeof(uint32_t) : 16, st));
     BinTree bt;
     bt.n = n;
@@ -168,6 +171,8 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
     bt.count = m_count.as<uint32_t>();
     bt.box = m_box.as<float>();
     bt.visits = m_visits.as<uint32_t>();
+    bt.cost = m_cost.as<float>();
+    bt.split = m_split.as<uint8_t>();
     if (n_inner) k_lbvh_node<<<div_up(n_inner, kBuildBlock), kBuildBlock, 0, st>>>(n_inner, keys, bt);
     k_lbvh_refit<<<div_up(n, kBuildBlock), kBuildBlock, 0, st>>>(n, tris60, sorted_idx, g->pad, bt);
 
@@ -229,9 +234,9 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
     cudaEventDestroy(e1);
     CRT_CUDA(cudaGetLastError());
     ctx->launches += 5 + depth;
-    if (depth > kStackSize)
+    if (2 * depth > kStackSize)
     {
-        set_error("wide BVH depth %d exceeds the traversal stack (%d)", depth, kStackSize);
+        set_error("wide BVH depth %d exceeds the traversal stack (%d entries, two per level)", depth, kStackSize);
         return CRT_ESTACK;
     }
     return CRT_OK;
@@ -330,6 +335,7 @@ extern "C" int crt_destroy_geometry(crt_ctx* ctx, crt_geometry g)
     CRT_CUDA(cudaSetDevice(g->device));
     CRT_CUDA(cudaFree(g->nodes));
     CRT_CUDA(cudaFree(g->tris));
+    if (g->light_table) CRT_CUDA(cudaFree(g->light_table));
     delete g;
     return CRT_OK;
 }

@@ -8,7 +8,7 @@
 // warp stay coherent and the Gaussian neighbourhoods of a block overlap in L1.  Randomness is keyed on
 // (xi, yi, frame, stage), so the mapping does not change any result.
 #include "ctx.cuh"
-#include "restir_pixel.cuh"
+#include "shadow_queue.cuh"
 
 namespace crt
 {
@@ -50,12 +50,31 @@ __global__ void __launch_bounds__(256) k_raycast(int W, int H, Rows rows, Bvh bv
     const TilePix t = this_pixel(W, H, rows);
     if (t.in) px_raycast(t.px, W, H, bvh, raygen, vis);
 }
+__device__ __forceinline__ ShadowRay to_shadow_ray(const DeferredRay& d, int pix)
+{
+    ShadowRay r;
+    r.ox = d.org.x; r.oy = d.org.y; r.oz = d.org.z;
+    r.pix = (uint32_t)pix;
+    r.dx = d.dir.x; r.dy = d.dir.y; r.dz = d.dir.z;
+    r.ucw = 0.0f;
+    r.bgx = r.bgy = r.bgz = r.pad0 = r.rx = r.ry = r.rz = r.pad1 = 0.0f;
+    return r;
+}
+// WF: emit the visibility-reuse ray into the queue instead of walking it here (shadow_queue.cuh)
+template <class L, bool WF>
 __global__ void __launch_bounds__(256)
     k_generate_candidate(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
-                         const uint32_t* lights, uint32_t n_lights, crt_options options, crt_reservoir* out)
+                         L lights, crt_options options, crt_reservoir* out, ShadowQueue q)
 {
     const TilePix t = this_pixel(W, H, rows);
-    if (t.in) px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, n_lights, make_opt(options), AosStore{out});
+    DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
+    if (t.in) d = px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, make_opt(options), AosStore{out}, WF);
+    if (WF) queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
+}
+__global__ void __launch_bounds__(256) k_build_light_table(uint32_t n, const float* tris60, const uint32_t* lights, LightRec* table)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) table[i] = make_light_rec(tris60, lights[i]);
 }
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -84,12 +103,25 @@ __global__ void __launch_bounds__(256)
         px_spatial<Math<MODE>>(t.px, W, H, frame, pass, bvh, tris60, vis, eye, make_opt(options),
                                AosStore{const_cast<crt_reservoir*>(in)}, AosStore{out});
 }
+template <bool WF>
 __global__ void __launch_bounds__(256)
     k_resolve(crt_float4* accum, int W, int H, Rows rows, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
-              crt_options options, const crt_reservoir* res)
+              crt_options options, const crt_reservoir* res, ShadowQueue q)
 {
     const TilePix t = this_pixel(W, H, rows);
-    if (t.in) px_resolve(t.px, accum, bvh, tris60, vis, eye, make_opt(options), AosStore{const_cast<crt_reservoir*>(res)});
+    DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
+    DeferredShade sh{{0, 0, 0}, {0, 0, 0}, 0.0f};
+    if (t.in)
+        d = px_resolve(t.px, accum, bvh, tris60, vis, eye, make_opt(options), AosStore{const_cast<crt_reservoir*>(res)},
+                       WF ? &sh : nullptr);
+    if (WF)
+    {
+        ShadowRay r = to_shadow_ray(d, t.px.idx);
+        r.ucw = sh.ucw;
+        r.bgx = sh.bg.x; r.bgy = sh.bg.y; r.bgz = sh.bg.z;
+        r.rx = sh.rad.x; r.ry = sh.rad.y; r.rz = sh.rad.z;
+        queue_push(q, d.want, r);
+    }
 }
 
 // ---- common/kernels/common.cu:4-17 and :30-74 (every pixel is touched: plain linear sweeps)
@@ -139,6 +171,59 @@ inline unsigned sweep_blocks(crt_ctx* ctx, size_t n)
 }
 }  // namespace
 
+// ---- wavefront plumbing
+static int queue_prepare(crt_ctx* ctx, size_t n_pixels, ShadowQueue* q)
+{
+    if (ctx->queue_capacity < n_pixels)
+    {
+        if (ctx->queue_rays) CRT_CUDA(cudaFree(ctx->queue_rays));
+        ctx->queue_rays = nullptr;
+        ctx->queue_capacity = 0;
+        CRT_CUDA(cudaMalloc(&ctx->queue_rays, n_pixels * sizeof(ShadowRay)));
+        ctx->queue_capacity = n_pixels;
+    }
+    if (!ctx->queue_counters) CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 2 * sizeof(unsigned)));
+    CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 2 * sizeof(unsigned), ctx->stream));
+    q->rays = (ShadowRay*)ctx->queue_rays;
+    q->count = ctx->queue_counters;
+    q->next = ctx->queue_counters + 1;
+    q->capacity = (uint32_t)ctx->queue_capacity;
+    return CRT_OK;
+}
+template <int EPI>
+static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, const ShadowSink& sink)
+{
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm)
+    {
+        CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_shadow_queue<EPI>, kShadowWarps * 32, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, ctx->stream>>>(geom->view(), q, sink);
+    return check_launch(ctx, "trace_shadow_queue");
+}
+// light records for (geometry, light list); rebuilt when another list is passed
+static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60, const uint32_t* lights, size_t n,
+                           const LightRec** out)
+{
+    if (geom->light_table_key != lights || geom->light_table_n != n)
+    {
+        if (geom->light_table) CRT_CUDA(cudaFree(geom->light_table));
+        geom->light_table = nullptr;
+        CRT_CUDA(cudaMalloc(&geom->light_table, (n ? n : 1) * sizeof(LightRec)));
+        if (n)
+        {
+            k_build_light_table<<<div_up(n, 256), 256, 0, ctx->stream>>>((uint32_t)n, tris60, lights, (LightRec*)geom->light_table);
+            const int rc = check_launch(ctx, "build_light_table");
+            if (rc != CRT_OK) return rc;
+        }
+        geom->light_table_key = lights;
+        geom->light_table_n = n;
+    }
+    *out = (const LightRec*)geom->light_table;
+    return CRT_OK;
+}
+
 #define CRT_CHECK_IMAGE(W, H) CRT_REQUIRE((W) > 0 && (H) > 0 && (size_t)(W) * (size_t)(H) < 0x7fffffffull, "bad image size")
 #define CRT_CHECK_BUF(b, n, what) CRT_REQUIRE((b).data != nullptr && bsize(b) >= (size_t)(n), what " buffer too small or null")
 
@@ -165,10 +250,37 @@ extern "C" int crt_generate_candidate(crt_ctx* ctx, int W, int H, int frame, crt
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
     CRT_REQUIRE(bsize(lights) < 0xffffffffull, "too many lights");
-    k_generate_candidate<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(
-        W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data, (const crt_visibility*)visibility_buffer.data,
-        to_f3(eye), (const uint32_t*)lights.data, (uint32_t)bsize(lights), options, (crt_reservoir*)reservoirs.data);
-    return check_launch(ctx, "generate_candidate");
+    const Rows rows = rows_of(ctx, H);
+    const float* tris60 = (const float*)triangles.data;
+    const crt_visibility* vis = (const crt_visibility*)visibility_buffer.data;
+    crt_reservoir* res = (crt_reservoir*)reservoirs.data;
+    const uint32_t n_lights = (uint32_t)bsize(lights);
+    const bool wf = ctx->wavefront && options.use_visibility_reuse;
+    ShadowQueue q{nullptr, nullptr, nullptr, 0};
+    if (wf)
+    {
+        const int rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
+        if (rc != CRT_OK) return rc;
+    }
+    const dim3 grid = tile_grid(W, rows);
+    if (ctx->light_table)
+    {
+        const LightRec* table = nullptr;
+        const int rc = light_table_for(ctx, geom, tris60, (const uint32_t*)lights.data, n_lights, &table);
+        if (rc != CRT_OK) return rc;
+        const LightsTable L{table, n_lights};
+        if (wf) k_generate_candidate<LightsTable, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
+        else k_generate_candidate<LightsTable, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
+    }
+    else
+    {
+        const LightsIndexed L{tris60, (const uint32_t*)lights.data, n_lights};
+        if (wf) k_generate_candidate<LightsIndexed, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
+        else k_generate_candidate<LightsIndexed, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
+    }
+    int rc = check_launch(ctx, "generate_candidate");
+    if (rc != CRT_OK || !wf) return rc;
+    return queue_trace<kEpiReservoirVisibility>(ctx, geom, q, ShadowSink{res, nullptr, 0});
 }
 
 extern "C" int crt_temporal_resampling(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
@@ -234,10 +346,23 @@ extern "C" int crt_resolve(crt_ctx* ctx, crt_buffer accumulation, int W, int H, 
     CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
     CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
-    k_resolve<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>((crt_float4*)accumulation.data, W, H, rows_of(ctx, H), geom->view(),
-                                                       (const float*)triangles.data,
-                                                       (const crt_visibility*)visibility_buffer.data, to_f3(eye),
-                                                       options, (const crt_reservoir*)reservoirs.data);
+    const Rows rows = rows_of(ctx, H);
+    crt_float4* accum = (crt_float4*)accumulation.data;
+    ShadowQueue q{nullptr, nullptr, nullptr, 0};
+    if (ctx->wavefront)
+    {
+        int rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
+        if (rc != CRT_OK) return rc;
+        k_resolve<true><<<tile_grid(W, rows), 256, 0, ctx->stream>>>(accum, W, H, rows, geom->view(), (const float*)triangles.data,
+                                                                    (const crt_visibility*)visibility_buffer.data, to_f3(eye),
+                                                                    options, (const crt_reservoir*)reservoirs.data, q);
+        rc = check_launch(ctx, "resolve");
+        if (rc != CRT_OK) return rc;
+        return queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate});
+    }
+    k_resolve<false><<<tile_grid(W, rows), 256, 0, ctx->stream>>>(accum, W, H, rows, geom->view(), (const float*)triangles.data,
+                                                                 (const crt_visibility*)visibility_buffer.data, to_f3(eye),
+                                                                 options, (const crt_reservoir*)reservoirs.data, q);
     return check_launch(ctx, "resolve");
 }
 

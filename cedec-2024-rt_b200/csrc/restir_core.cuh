@@ -91,24 +91,69 @@ struct LightSample
     f3 p, n, emissive;
     float area;
 };
-// core.hpp:261-285 plus what the callers read from the same triangle (emissive, area_of)
-CRT_HD LightSample sample_light(const float* tris60, const uint32_t* lights, uint32_t n_lights, float rv0, float rv1,
-                                float rv2)
+// core.hpp:261-285 plus what the callers read from the same triangle (emissive, area_of).
+// Two interchangeable sources with identical results:
+//   LightsIndexed  the reference's double indirection lights[nth] -> triangles[index] (60-byte AoS gather)
+//   LightsTable    a 64-byte record per light, built once per (geometry, light list): vertices, the normal and
+//                  area the reference recomputes per candidate (same operations, so the same bits), emission
+struct LightsIndexed
 {
-    uint32_t nth = (uint32_t)(rv0 * (float)n_lights);
-    if (nth == n_lights) nth = n_lights - 1;
-    const TriRef t = tri_at(tris60, (int)CRT_LDG(lights + nth));
-    const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2);
-    const f2 b = warp_unit_triangle(rv1, rv2);
-    LightSample ls;
-    ls.p = bary_point(v0, v1, v2, b.x, b.y);
+    const float* tris60;
+    const uint32_t* lights;
+    uint32_t n;
+    CRT_HD LightSample sample(float rv0, float rv1, float rv2) const
+    {
+        uint32_t nth = (uint32_t)(rv0 * (float)n);
+        if (nth == n) nth = n - 1;
+        const TriRef t = tri_at(tris60, (int)CRT_LDG(lights + nth));
+        const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2);
+        const f2 b = warp_unit_triangle(rv1, rv2);
+        LightSample ls;
+        ls.p = bary_point(v0, v1, v2, b.x, b.y);
+        const f3 c = cross(v1 - v0, v2 - v0);
+        const float len = length(c);
+        ls.n = c / len;        // normal_of
+        ls.area = 0.5f * len;  // area_of
+        ls.emissive = t.emissive();
+        return ls;
+    }
+};
+struct alignas(16) LightRec  // 64 bytes
+{
+    float v0x, v0y, v0z, area;
+    float v1x, v1y, v1z, nx;
+    float v2x, v2y, v2z, ny;
+    float ex, ey, ez, nz;
+};
+CRT_HD LightRec make_light_rec(const float* tris60, uint32_t tri_index)
+{
+    const TriRef t = tri_at(tris60, (int)tri_index);
+    const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2), e = t.emissive();
     const f3 c = cross(v1 - v0, v2 - v0);
     const float len = length(c);
-    ls.n = c / len;            // normal_of
-    ls.area = 0.5f * len;      // area_of
-    ls.emissive = t.emissive();
-    return ls;
+    const f3 n = c / len;
+    return LightRec{v0.x, v0.y, v0.z, 0.5f * len, v1.x, v1.y, v1.z, n.x, v2.x, v2.y, v2.z, n.y, e.x, e.y, e.z, n.z};
 }
+struct LightsTable
+{
+    const LightRec* table;
+    uint32_t n;
+    CRT_HD LightSample sample(float rv0, float rv1, float rv2) const
+    {
+        uint32_t nth = (uint32_t)(rv0 * (float)n);
+        if (nth == n) nth = n - 1;
+        const char* q = (const char*)(table + nth);
+        const u4 a = load_u4(q), b4 = load_u4(q + 16), c4 = load_u4(q + 32), d = load_u4(q + 48);
+        const f3 v0{u2f(a.x), u2f(a.y), u2f(a.z)}, v1{u2f(b4.x), u2f(b4.y), u2f(b4.z)}, v2{u2f(c4.x), u2f(c4.y), u2f(c4.z)};
+        const f2 b = warp_unit_triangle(rv1, rv2);
+        LightSample ls;
+        ls.p = bary_point(v0, v1, v2, b.x, b.y);
+        ls.n = f3{u2f(b4.w), u2f(c4.w), u2f(d.w)};
+        ls.area = u2f(a.w);
+        ls.emissive = f3{u2f(d.x), u2f(d.y), u2f(d.z)};
+        return ls;
+    }
+};
 CRT_HD float geometry_term(f3 p0, f3 n0, f3 p1, f3 n1)  // core.hpp:287-295
 {
     f3 v = p1 - p0;
@@ -191,17 +236,17 @@ CRT_HD Opt make_opt(const crt_options& o)
 
 // RIS over the emissive triangles: generate_candidate (10_restir_di.cu:78-111) and 09_ris.cu:66-100.
 // Randoms are drawn left to right: light pick, two barycentric randoms, then the reservoir's u.
-CRT_HD Res ris_candidates(const Bvh& bvh, const float* tris60, const Surf& surf, const uint32_t* lights,
-                          uint32_t n_lights, int count, bool shadowed, Pcg& rng)
+template <class L>
+CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int count, bool shadowed, Pcg& rng)
 {
     Res r = empty_res();
-    const float inv_n = 1.0f / (float)n_lights;
+    const float inv_n = 1.0f / (float)lights.n;
     for (int i = 0; i < count; ++i)
     {
         const float r0 = rng.next_f();
         const float r1 = rng.next_f();
         const float r2 = rng.next_f();
-        const LightSample ls = sample_light(tris60, lights, n_lights, r0, r1, r2);
+        const LightSample ls = lights.sample(r0, r1, r2);
         const float light_pdf = inv_n * 1.0f / ls.area;  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
         const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
         const float weight = p_hat / light_pdf;

@@ -94,30 +94,46 @@ CRT_HD void px_raycast(const Pix& px, int W, int H, const Bvh& bvh, const crt_ra
     store_vis(vis, px.idx, h);
 }
 
-// ---- 10_restir_di.cu:36-135
-template <class RS>
-CRT_HD void px_generate_candidate(const Pix& px, int frame, const Bvh& bvh, const float* tris60,
-                                  const crt_visibility* vis, f3 eye, const uint32_t* lights, uint32_t n_lights,
-                                  const Opt& opt, const RS& out)
+// A shadow ray the caller traces later (wavefront mode, shadow_queue.cuh): check_visibility's segment
+// (raytrace.hpp:45-52) — origin p0 + 1e-3 n0, direction p1 - p0, t in [0, 0.99].
+struct DeferredRay
 {
+    bool want;
+    f3 org, dir;
+};
+CRT_HD DeferredRay visibility_ray(f3 p0, f3 n0, f3 p1) { return DeferredRay{true, p0 + 0.001f * n0, p1 - p0}; }
+
+// ---- 10_restir_di.cu:36-135.  With `defer` the visibility-reuse ray is returned instead of traced and the
+// reservoir is stored with visibility = false for the trace kernel to fill in.
+template <class L, class RS>
+CRT_HD DeferredRay px_generate_candidate(const Pix& px, int frame, const Bvh& bvh, const float* tris60,
+                                         const crt_visibility* vis, f3 eye, const L& lights, const Opt& opt,
+                                         const RS& out, bool defer = false)
+{
+    DeferredRay ray{false, {0, 0, 0}, {0, 0, 0}};
     const Vis v = load_vis(vis, px.idx);
     if (v.index == -1)
     {
         out.store(px.idx, empty_res());
-        return;
+        return ray;
     }
     const TriRef tri = tri_at(tris60, v.index);
     if (has_emission(tri.emissive()))
     {
         out.store(px.idx, empty_res());
-        return;
+        return ray;
     }
     Pcg rng(hash_pcg4(px.xi, px.yi, frame, 0), 0);
     const Surf surf = surface_from_visibility(tri, v.u, v.v, eye);
-    Res r = ris_candidates(bvh, tris60, surf, lights, n_lights, opt.ris_count, false, rng);
+    Res r = ris_candidates(bvh, lights, surf, opt.ris_count, false, rng);
     r.ucw = ucw_of(r, target_function(bvh, surf.p, surf.n, r.s.hp, r.s.hn, r.s.rad, opt.shadowed));
-    if (opt.reuse) r.s.vis = check_visibility(bvh, surf.p, surf.n, r.s.hp) != 0.0f ? 1u : 0u;
+    if (opt.reuse)
+    {
+        if (defer) ray = visibility_ray(surf.p, surf.n, r.s.hp);
+        else r.s.vis = check_visibility(bvh, surf.p, surf.n, r.s.hp) != 0.0f ? 1u : 0u;
+    }
     out.store(px.idx, r);
+    return ray;
 }
 
 // ---- 10_restir_di.cu:137-237
@@ -181,26 +197,43 @@ CRT_HD void write_accum(crt_float4* accum, int idx, f3 c, bool add)
     }
     accum[idx] = a;
 }
-template <class RS>
-CRT_HD void px_resolve(const Pix& px, crt_float4* accum, const Bvh& bvh, const float* tris60,
-                       const crt_visibility* vis, f3 eye, const Opt& opt, const RS& res)
+// With `shade` non-null the shadow ray is returned instead of traced, together with the factors of
+// radiance = brdf * G * V * sample.radiance * ucw that the trace kernel multiplies out (shade->bg = brdf * G).
+struct DeferredShade
 {
+    f3 bg, rad;
+    float ucw;
+};
+template <class RS>
+CRT_HD DeferredRay px_resolve(const Pix& px, crt_float4* accum, const Bvh& bvh, const float* tris60,
+                              const crt_visibility* vis, f3 eye, const Opt& opt, const RS& res,
+                              DeferredShade* shade = nullptr)
+{
+    DeferredRay ray{false, {0, 0, 0}, {0, 0, 0}};
     const Vis v = load_vis(vis, px.idx);
     if (v.index == -1)
     {
         accum[px.idx] = {0.0f, 0.0f, 0.0f, 1.0f};  // assigned even when accumulating
-        return;
+        return ray;
     }
     const TriRef tri = tri_at(tris60, v.index);
     const f3 em = tri.emissive();
     if (has_emission(em))
     {
         accum[px.idx] = {em.x, em.y, em.z, 1.0f};
-        return;
+        return ray;
     }
     const Surf surf = surface_from_visibility(tri, v.u, v.v, eye);
     const Res r = res.load(px.idx);
+    if (shade)
+    {
+        shade->bg = (kInvPi * tri.color()) * geometry_term(surf.p, surf.n, r.s.hp, r.s.hn);
+        shade->rad = r.s.rad;
+        shade->ucw = r.ucw;
+        return visibility_ray(surf.p, surf.n, r.s.hp);
+    }
     write_accum(accum, px.idx, resolve_radiance(bvh, surf, tri.color(), r), opt.accumulate);
+    return ray;
 }
 
 // ---- 07_pt.cu:11-90 (EX = 7), 08_nee.cu:11-129 (EX = 8), 09_ris.cu:11-166 (EX = 9)
@@ -235,7 +268,7 @@ CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh
             const float r0 = rng.next_f();
             const float r1 = rng.next_f();
             const float r2 = rng.next_f();
-            const LightSample ls = sample_light(tris60, lights, n_lights, r0, r1, r2);
+            const LightSample ls = LightsIndexed{tris60, lights, n_lights}.sample(r0, r1, r2);
             const float V = check_visibility(bvh, surf.p, surf.n, ls.p);
             const f3 brdf = kInvPi * color;
             const float G = geometry_term(surf.p, surf.n, ls.p, ls.n);
@@ -244,7 +277,7 @@ CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh
         }
         else if (EX == 9)
         {
-            const Res r = ris_candidates(bvh, tris60, surf, lights, n_lights, opt.ris_count, opt.shadowed, rng);
+            const Res r = ris_candidates(bvh, LightsIndexed{tris60, lights, n_lights}, surf, opt.ris_count, opt.shadowed, rng);
             const f3 brdf = kInvPi * color;
             const float G = geometry_term(surf.p, surf.n, r.s.hp, r.s.hn);
             const float V = check_visibility(bvh, surf.p, surf.n, r.s.hp);

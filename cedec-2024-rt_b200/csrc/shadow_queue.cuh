@@ -1,0 +1,280 @@
+// shadow_queue.cuh — wavefront shadow rays: a compacted ray queue and a persistent-warp any-hit kernel.
+//
+// check_visibility() (common/raytrace.hpp:45-52) is called once per diffuse pixel by generate_candidate
+// (visibility reuse, 10_restir_di.cu:127-131) and once by resolve (:443-444).  The rays go from coherent
+// pixels to randomly chosen lights anywhere in the scene, so their walks have very different lengths:
+// traced inside the per-pixel kernels, a warp ran at 9 of 32 lanes (profiles/r1/source_a_k_resolve.txt).
+// Here the per-pixel kernel only *emits* the ray (warp-aggregated append, 64-byte record), and a
+// persistent kernel — one resident set of warps per SM, rays fetched from a global counter — walks them;
+// a lane that finishes takes the next ray as soon as fewer than kRefillThreshold lanes of its warp are
+// still busy, so the warps stay full.  The result is written where the per-pixel code would have put it
+// (the reservoir's visibility byte, or the shaded pixel), bit for bit.
+#pragma once
+#include "restir_pixel.cuh"
+
+namespace crt
+{
+// 64-byte ray record: four 16-byte words
+struct alignas(16) ShadowRay
+{
+    float ox, oy, oz;   // origin  p0 + 1e-3 n0
+    uint32_t pix;       // pixel index the result belongs to
+    float dx, dy, dz;   // direction p1 - p0 (t in [0, 0.99])
+    float ucw;          // resolve: reservoir.ucw
+    float bgx, bgy, bgz;  // resolve: brdf * G
+    float pad0;
+    float rx, ry, rz;   // resolve: reservoir.sample.radiance
+    float pad1;
+};
+static_assert(sizeof(ShadowRay) == 64, "ShadowRay must be 64 bytes");
+
+struct ShadowQueue
+{
+    ShadowRay* rays;
+    uint32_t* count;   // rays appended so far
+    uint32_t* next;    // next ray to fetch (persistent kernel)
+    uint32_t capacity;
+};
+
+constexpr int kRefillThreshold = 24;  // refetch when fewer lanes than this are still walking
+
+#if defined(__CUDACC__)
+// warp-aggregated append; every lane of the warp must call it (has = whether this lane emits a ray)
+__device__ __forceinline__ void queue_push(const ShadowQueue& q, bool has, const ShadowRay& ray)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, has);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(q.count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (has)
+    {
+        const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        float4* dst = (float4*)(q.rays + slot);
+        dst[0] = make_float4(ray.ox, ray.oy, ray.oz, __uint_as_float(ray.pix));
+        dst[1] = make_float4(ray.dx, ray.dy, ray.dz, ray.ucw);
+        dst[2] = make_float4(ray.bgx, ray.bgy, ray.bgz, 0.0f);
+        dst[3] = make_float4(ray.rx, ray.ry, ray.rz, 0.0f);
+    }
+}
+
+enum
+{
+    kEpiReservoirVisibility = 0,  // reservoirs[pix].sample.visibility = !occluded   (generate_candidate)
+    kEpiResolve = 1               // accumulation[pix] (+)= brdf*G*V*radiance*ucw     (resolve)
+};
+
+struct ShadowSink
+{
+    crt_reservoir* reservoirs;  // kEpiReservoirVisibility
+    crt_float4* accumulation;   // kEpiResolve
+    int accumulate;
+};
+
+// the shading factors stay in the queue record until the ray is decided (keeps the walk's register count down)
+template <int EPI>
+__device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const ShadowRay* rec, uint32_t pix,
+                                                bool occluded)
+{
+    if (EPI == kEpiReservoirVisibility)
+    {
+        // word 15 of the 19-word Reservoir holds `bool visibility` (+ 3 padding bytes)
+        ((uint32_t*)(sink.reservoirs + pix))[15] = occluded ? 0u : 1u;
+    }
+    else
+    {
+        // radiance = brdf * G * V * sample.radiance * ucw, evaluated left to right (10_restir_di.cu:446-447)
+        const float4* src = (const float4*)rec;
+        const float4 w1 = __ldcs(src + 1), w2 = __ldcs(src + 2), w3 = __ldcs(src + 3);
+        const float V = occluded ? 0.0f : 1.0f;
+        const f3 bg{w2.x, w2.y, w2.z}, rad{w3.x, w3.y, w3.z};
+        const f3 c = bg * V * rad * w1.w;
+        write_accum(sink.accumulation, (int)pix, c, sink.accumulate != 0);
+    }
+}
+
+// One node step of the any-hit walk (the node half of walk_step): pops / descends and leaves the hit
+// triangles of the visited node in w.tmask.  Returns false when the walk has nothing left (a miss).
+__device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, const RaySetup& r)
+{
+    if ((w.ng_mask >> 24) == 0)
+    {
+        if (w.sp == 0) return false;
+        --w.sp;
+        w.ng_base = w.stack_base[w.sp];
+        w.ng_mask = w.stack_mask[w.sp];
+    }
+    const int bit = 31 - __clz((int)w.ng_mask);
+    w.ng_mask &= ~(1u << bit);
+    const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+    const uint32_t node_idx = w.ng_base + (uint32_t)__popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
+    if (w.ng_mask >> 24)
+    {
+        w.stack_base[w.sp] = w.ng_base;
+        w.stack_mask[w.sp] = w.ng_mask;
+        ++w.sp;
+    }
+    uint32_t imask;
+    const uint32_t hits = intersect_node(bvh, node_idx, r, 0.0f, 0.99f, w.ng_base, w.tri_base, imask);
+    w.ng_mask = (hits & 0xff000000u) | imask;
+    w.tmask = hits & 0x00ffffffu;
+    return true;
+}
+
+constexpr int kShadowWarps = 4;    // warps per block of the persistent kernel
+constexpr int kPairCap = 128;      // (ray, triangle) pairs a warp tests per cooperative round trip
+
+// Persistent any-hit walk over the queue.  Launch with (resident blocks per SM) x (SM count) blocks.
+//
+// Each iteration has two warp-wide phases:
+//   node phase      every walking lane takes one node step of its own ray (8 child boxes);
+//   triangle phase  the (ray, triangle) pairs the node steps produced — a few lanes own a few triangles each —
+//                   are pooled in shared memory and dealt out evenly to all 32 lanes; a lane tests a triangle
+//                   against the *owner's* ray (fetched with shuffles) and reports an occlusion by setting the
+//                   owner's bit.  Without pooling the ~100-instruction triangle test ran with 3 of 32 lanes
+//                   (profiles/r1/source_c_trace_shadow_queue.txt).
+// A lane whose ray is decided takes the next ray from the global counter as soon as fewer than
+// kRefillThreshold lanes of its warp are still walking.
+template <int EPI>
+__global__ void __launch_bounds__(kShadowWarps * 32, 6) k_trace_shadow_queue(Bvh bvh, ShadowQueue q, ShadowSink sink)
+{
+    __shared__ uint32_t s_pairs[kShadowWarps][kPairCap];
+    __shared__ uint32_t s_occluded[kShadowWarps];
+    const uint32_t n_rays = *q.count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    uint32_t* pairs = s_pairs[warp];
+    if (lane == 0) s_occluded[warp] = 0u;
+    __syncwarp();
+
+    bool active = false, exhausted = false;
+    RaySetup r;
+    r.ro = r.rd = f3{0.0f, 0.0f, 0.0f};
+    uint32_t pix = 0, ray_idx = 0;
+    Walk w;
+    w.sp = 0;
+    w.ng_base = w.ng_mask = w.tri_base = w.tmask = 0;
+
+    for (;;)
+    {
+        // ---- refill idle lanes from the global counter
+        if (!exhausted)
+        {
+            const unsigned idle = __ballot_sync(full, !active);
+            if (idle)
+            {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(q.next, (uint32_t)__popc(idle));
+                base = __shfl_sync(full, base, leader);
+                if (!active)
+                {
+                    const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                    if (my < n_rays)
+                    {
+                        const float4* src = (const float4*)(q.rays + my);
+                        const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
+                        pix = __float_as_uint(w0.w);
+                        ray_idx = my;
+                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z});
+                        walk_begin(w, r);
+                        active = true;
+                    }
+                }
+                if (base + (uint32_t)__popc(idle) >= n_rays) exhausted = true;  // warp-uniform
+            }
+        }
+        unsigned act = __ballot_sync(full, active);
+        if (act == 0) break;
+
+        // ---- walk until the warp thins out
+        for (;;)
+        {
+            // node phase
+            bool missed = false;
+            if (active) missed = !shadow_node_step(bvh, w, r);
+            // triangle phase: pool the pairs of the whole warp
+            const uint32_t cnt = active ? (uint32_t)__popc(w.tmask) : 0u;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t v = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t total = __shfl_sync(full, incl, 31);
+            uint32_t pos = incl - cnt;  // this lane's first pair
+            for (uint32_t chunk = 0; chunk < total; chunk += kPairCap)
+            {
+                // owners publish (owner lane, triangle record) for the pairs that fall into this chunk
+                uint32_t m = w.tmask;
+                uint32_t p = pos;
+                while (m && p < chunk + kPairCap)
+                {
+                    const int i = __ffs((int)m) - 1;
+                    if (p >= chunk)
+                    {
+                        pairs[p - chunk] = ((uint32_t)lane << 27) | (w.tri_base + (uint32_t)i);
+                        m &= m - 1u;
+                        ++p;
+                    }
+                    else
+                    {
+                        m &= m - 1u;
+                        ++p;
+                    }
+                }
+                // (pairs below `chunk` were handled in an earlier round: drop them from the owner's mask)
+                w.tmask = m;
+                pos = p;
+                __syncwarp();
+                const uint32_t n_here = min(total - chunk, (uint32_t)kPairCap);
+                for (uint32_t k0 = 0; k0 < n_here; k0 += 32)
+                {
+                    const uint32_t k = k0 + (uint32_t)lane;
+                    const bool valid = k < n_here;
+                    const uint32_t pr = valid ? pairs[k] : ((uint32_t)lane << 27);
+                    const int owner = (int)(pr >> 27);
+                    RaySetup o;
+                    o.ro.x = __shfl_sync(full, r.ro.x, owner);
+                    o.ro.y = __shfl_sync(full, r.ro.y, owner);
+                    o.ro.z = __shfl_sync(full, r.ro.z, owner);
+                    o.rd.x = __shfl_sync(full, r.rd.x, owner);
+                    o.rd.y = __shfl_sync(full, r.rd.y, owner);
+                    o.rd.z = __shfl_sync(full, r.rd.z, owner);
+                    if (valid)
+                    {
+                        Hit h;
+                        h.prim = -1;
+                        h.t = 0.99f;
+                        h.u = h.v = 0.0f;
+                        if (intersect_wide_tri(bvh.tris + (pr & 0x07ffffffu), o, 0.0f, h))
+                            atomicOr(&s_occluded[warp], 1u << owner);
+                    }
+                }
+                __syncwarp();
+            }
+            w.tmask = 0;
+            const uint32_t occ = s_occluded[warp];
+            __syncwarp();
+            if (lane == 0) s_occluded[warp] = 0u;
+            __syncwarp();
+            if (active)
+            {
+                const bool occluded = (occ >> lane) & 1u;
+                if (occluded || missed)
+                {
+                    shadow_epilogue<EPI>(sink, q.rays + ray_idx, pix, occluded);
+                    active = false;
+                }
+            }
+            act = __ballot_sync(full, active);
+            if (act == 0) break;
+            if (!exhausted && __popc(act) < kRefillThreshold) break;
+        }
+    }
+}
+#endif  // __CUDACC__
+}  // namespace crt

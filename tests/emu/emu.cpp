@@ -19,6 +19,36 @@
 
 using namespace crt;
 
+namespace crt
+{
+int g_emu_postpone = 0;
+}
+extern "C" void emu_set_postpone(int v) { crt::g_emu_postpone = v; }
+
+#if defined(CRT_COUNT)
+namespace crt
+{
+thread_local unsigned long long g_count_nodes = 0, g_count_tris = 0;
+}
+static unsigned long long g_total_nodes = 0, g_total_tris = 0;
+extern "C" void emu_counters(unsigned long long* out, int reset)
+{
+    // fold every OpenMP thread's counters into the totals
+#pragma omp parallel
+    {
+#pragma omp critical
+        {
+            g_total_nodes += crt::g_count_nodes;
+            g_total_tris += crt::g_count_tris;
+            crt::g_count_nodes = crt::g_count_tris = 0;
+        }
+    }
+    out[0] = g_total_nodes;
+    out[1] = g_total_tris;
+    if (reset) g_total_nodes = g_total_tris = 0;
+}
+#endif
+
 namespace
 {
 struct EmuGeom
@@ -28,7 +58,7 @@ struct EmuGeom
     const float* tris60 = nullptr;
     int depth = 0;
     float pad = 0;
-    Bvh view() const { return Bvh{nodes.data(), tris.data()}; }
+    Bvh view() const { return Bvh{nodes.data(), tris.data(), kPostponeRatio}; }
 };
 int g_math_mode = 0;
 long g_tid_begin = 0, g_tid_end = -1;
@@ -75,8 +105,10 @@ EmuGeom* build(const float* tris60, uint32_t n)
     const uint32_t ni = n - 1;
     std::vector<uint32_t> left(ni + 1), right(ni + 1), parent(2 * (size_t)n - 1), first(ni + 1), count(ni + 1),
         visits(ni + 1, 0u);
-    std::vector<float> box((2 * (size_t)n - 1) * 6);
-    BinTree bt{n, left.data(), right.data(), parent.data(), first.data(), count.data(), box.data(), visits.data()};
+    std::vector<float> box((2 * (size_t)n - 1) * 6), cost((2 * (size_t)n - 1) * 7);
+    std::vector<uint8_t> split((2 * (size_t)n - 1) * 8);
+    BinTree bt{n, left.data(), right.data(), parent.data(), first.data(), count.data(), box.data(), visits.data(),
+               cost.data(), split.data()};
     for (uint32_t i = 0; i < ni; i++) lbvh_node(i, skeys.data(), bt);
     for (uint32_t i = 0; i < n; i++) lbvh_refit(i, tris60, idx.data(), g->pad, bt);
 
@@ -184,8 +216,9 @@ extern "C"
         const Bvh bvh = ((EmuGeom*)gp)->view();
         launch(W, H, [&](Pix p)
                {
-                   px_generate_candidate(p, frame, bvh, (const float*)tris, vis, v3(eye), lights, (uint32_t)nlights,
-                                         make_opt(*opt), AosStore{res});
+                   px_generate_candidate(p, frame, bvh, (const float*)tris, vis, v3(eye),
+                                         LightsIndexed{(const float*)tris, lights, (uint32_t)nlights}, make_opt(*opt),
+                                         AosStore{res});
                });
     }
     void orc_temporal_resampling(int W, int H, int frame, void* gp, const crt_triangle* tris, int,

@@ -136,6 +136,13 @@ def test_wide_bvh_equals_brute_force(emu, port):
                                          tuv2.ctypes.data)
         assert idx == idx2 and (idx < 0 or same(tuv, tuv2)), (i, o, d)
         assert emu.lib.emu_any_hit(g, o.ctypes.data, d.ctypes.data, 0.0, tmax) == (1 if idx2 >= 0 else 0)
+        # the same walk with triangle groups postponed whenever the walk allows it (the divergence control of
+        # the CUDA path; any visiting order must give the same closest hit)
+        emu.lib.emu_set_postpone(1)
+        idx3, tuv3 = emu.closest_hit(g, o, d, 0.0, tmax)
+        any3 = emu.lib.emu_any_hit(g, o.ctypes.data, d.ctypes.data, 0.0, tmax)
+        emu.lib.emu_set_postpone(0)
+        assert idx3 == idx2 and (idx3 < 0 or same(tuv3, tuv2)) and any3 == (1 if idx2 >= 0 else 0)
         hits += idx >= 0
     assert hits > 100
     emu.geom_free(g)
