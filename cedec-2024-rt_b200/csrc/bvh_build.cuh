@@ -3,7 +3,8 @@
 //
 //   1 tri_bounds      triangle AABB + scene bounds (atomic min/max)
 //   2 morton_key      63-bit Morton code of the centroid            -> radix sort (cub)
-//   3 lbvh_node       Karras 2012 binary radix tree, one inner node per thread
+//   3 ploc_*          binary tree by parallel locally-ordered clustering (default), or
+//     lbvh_node       Karras 2012 binary radix tree, one inner node per thread (CRT_BVH_BUILDER=lbvh)
 //   4 lbvh_refit      bottom-up boxes (second arrival at a node continues) and, in the same sweep, the
 //                     SAH-optimal way to cut every subtree into at most i = 1..7 wide-BVH children
 //                     (dynamic programme of Ylitie et al. 2017, section 3.1)
@@ -128,6 +129,8 @@ struct BinTree
     float* cost;        // [2n-1][7]  c(node, i): least SAH cost of the subtree as a forest of <= i wide-BVH children
     uint8_t* split;     // [2n-1][8]  [0]: 1 = c(node,1) is a leaf; [j-1], j = 2..8: triangles... see sah_plan_node
 };
+
+CRT_HD uint32_t bin_tri_count(const BinTree& bt, uint32_t id) { return id >= bt.n - 1 ? 1u : bt.count[id]; }
 
 // SAH constants: one node step (8 child boxes) vs one triangle test, as in Ylitie et al. 2017
 constexpr float kCostNode = 1.0f, kCostTri = 0.3f, kCostInf = 1.0e30f;
@@ -284,6 +287,103 @@ CRT_HD void lbvh_refit(uint32_t leaf, const float* tris60, const uint32_t* sorte
     }
 }
 
+// ---- steps 3'/4' (default builder): PLOC — parallel locally-ordered clustering (Meister & Bittner 2018).
+// Clusters start as the Morton-sorted triangles.  Each round every cluster looks kPlocRadius positions to either
+// side for the neighbour whose union box has the smallest area; mutual nearest neighbours merge into a new inner
+// node (box, triangle count and SAH plan are final at that moment), the array is compacted, repeat until one
+// cluster is left.  Agglomerative clustering follows surface area, so the topology is much closer to a SAH
+// build than the Morton-prefix splits of the LBVH; the binary tree feeds the same collapse.
+constexpr int kPlocRadius = 16;
+
+struct PlocRound
+{
+    uint32_t m;              // clusters this round
+    const uint32_t* node_in; // [m] binary node id of each cluster
+    const float* box_in;     // [m][8] lo.xyz, -, hi.xyz, -
+    uint32_t* nn;            // [m] nearest neighbour position
+    unsigned long long* flag;// [m] low word: cluster survives (1/0); high word: it leads a merge (1/0)
+    uint32_t* node_out;      // [<= m]
+    float* box_out;
+};
+
+CRT_HD void ploc_init_leaf(uint32_t j, const float* tris60, const uint32_t* sorted_idx, float pad, const BinTree& bt,
+                           uint32_t* node_out, float* box_out)
+{
+    Aabb b = tri_aabb(load_build_tri(tris60, sorted_idx[j]));
+    b.lo = b.lo - f3{pad, pad, pad};
+    b.hi = b.hi + f3{pad, pad, pad};
+    const uint32_t id = (bt.n - 1) + j;
+    store_box(bt.box, id, b);
+    sah_plan_leaf(bt, id, aabb_half_area(b));
+    node_out[j] = id;
+    float* q = box_out + (size_t)j * 8;
+    q[0] = b.lo.x; q[1] = b.lo.y; q[2] = b.lo.z; q[3] = 0.0f;
+    q[4] = b.hi.x; q[5] = b.hi.y; q[6] = b.hi.z; q[7] = 0.0f;
+}
+CRT_HD Aabb ploc_box(const float* box, uint32_t i)
+{
+    const float* q = box + (size_t)i * 8;
+    return {{q[0], q[1], q[2]}, {q[4], q[5], q[6]}};
+}
+// nearest neighbour by (union area, i ^ j): the key is symmetric in (i, j), so the globally best pair is always
+// mutual (every round merges at least one pair) and runs of identical boxes pair up (i, i^1) instead of chaining
+CRT_HD void ploc_nn(uint32_t i, const PlocRound& p)
+{
+    const Aabb bi = ploc_box(p.box_in, i);
+    const uint32_t lo = i > (uint32_t)kPlocRadius ? i - kPlocRadius : 0u;
+    const uint32_t hi = i + kPlocRadius < p.m - 1 ? i + kPlocRadius : p.m - 1;
+    float best = 3.0e38f;
+    uint32_t best_j = i, best_x = 0xffffffffu;
+    for (uint32_t j = lo; j <= hi; j++)
+    {
+        if (j == i) continue;
+        const float a = aabb_half_area(aabb_union(bi, ploc_box(p.box_in, j)));
+        const uint32_t x = i ^ j;
+        if (a < best || (a == best && x < best_x))
+        {
+            best = a;
+            best_j = j;
+            best_x = x;
+        }
+    }
+    p.nn[i] = best_j;
+}
+CRT_HD void ploc_flag(uint32_t i, const PlocRound& p)
+{
+    const uint32_t j = p.nn[i];
+    const bool mutual = j != i && p.nn[j] == i;
+    const unsigned long long survive = (mutual && j < i) ? 0ull : 1ull;
+    const unsigned long long lead = (mutual && i < j) ? 1ull : 0ull;
+    p.flag[i] = survive | (lead << 32);
+}
+// scan[i] = exclusive prefix sum of flag; id_top = id of the first node created this round (ids count down to 0)
+CRT_HD void ploc_apply(uint32_t i, const PlocRound& p, const unsigned long long* scan, uint32_t id_top, const BinTree& bt)
+{
+    const unsigned long long f = p.flag[i];
+    if (!(f & 1ull)) return;
+    const uint32_t pos = (uint32_t)(scan[i] & 0xffffffffull);
+    uint32_t node = p.node_in[i];
+    Aabb b = ploc_box(p.box_in, i);
+    if (f >> 32)
+    {
+        const uint32_t j = p.nn[i];
+        const uint32_t id = id_top - (uint32_t)(scan[i] >> 32);
+        const uint32_t l = node, r = p.node_in[j];
+        b = aabb_union(b, ploc_box(p.box_in, j));
+        bt.left[id] = l;
+        bt.right[id] = r;
+        const uint32_t cnt = bin_tri_count(bt, l) + bin_tri_count(bt, r);
+        bt.count[id] = cnt;
+        store_box(bt.box, id, b);
+        sah_plan_node(bt, id, l, r, aabb_half_area(b), cnt);
+        node = id;
+    }
+    p.node_out[pos] = node;
+    float* q = p.box_out + (size_t)pos * 8;
+    q[0] = b.lo.x; q[1] = b.lo.y; q[2] = b.lo.z; q[3] = 0.0f;
+    q[4] = b.hi.x; q[5] = b.hi.y; q[6] = b.hi.z; q[7] = 0.0f;
+}
+
 // ---- step 5: collapse to the wide tree
 struct CollapseItem
 {
@@ -300,8 +400,24 @@ struct WideOut
     uint32_t* next_count;
 };
 
-CRT_HD uint32_t bin_tri_count(const BinTree& bt, uint32_t id) { return id >= bt.n - 1 ? 1u : bt.count[id]; }
-CRT_HD uint32_t bin_first(const BinTree& bt, uint32_t id) { return id >= bt.n - 1 ? id - (bt.n - 1) : bt.first[id]; }
+// sorted positions of the (<= 3) leaves under a binary node; PLOC subtrees are not contiguous ranges
+CRT_HD int bin_leaves(const BinTree& bt, uint32_t id, uint32_t out[kLeafMaxTris])
+{
+    uint32_t st[kLeafMaxTris + 1];
+    int sp = 0, n = 0;
+    st[sp++] = id;
+    while (sp)
+    {
+        const uint32_t x = st[--sp];
+        if (x >= bt.n - 1) out[n++] = x - (bt.n - 1);
+        else
+        {
+            st[sp++] = bt.right[x];
+            st[sp++] = bt.left[x];
+        }
+    }
+    return n;
+}
 
 CRT_HD uint8_t quant_exponent(float extent)
 {
@@ -472,10 +588,11 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
         else
         {
             wn.meta[s] = (uint8_t)((((1u << tc) - 1u) << 5) | tri_off);  // unary count
-            const uint32_t f = bin_first(bt, ch[k]);
+            uint32_t leaf_pos[kLeafMaxTris];
+            bin_leaves(bt, ch[k], leaf_pos);
             for (uint32_t j = 0; j < tc; j++)
             {
-                const uint32_t prim = sorted_idx[f + j];
+                const uint32_t prim = sorted_idx[leaf_pos[j]];
                 const BuildTri t = load_build_tri(tris60, prim);
                 WideTri wt;
                 wt.v0x = t.v0.x; wt.v0y = t.v0.y; wt.v0z = t.v0.z; wt.prim = (int32_t)prim;

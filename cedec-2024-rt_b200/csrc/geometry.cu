@@ -2,6 +2,7 @@
 // Replaces hiprtCreateContext + buildHiprtGeometry (10_restir_di.cpp:74-79,220; common/loader.hpp:68-112):
 // the BVH is built on the GPU from the device-resident reference Triangle array, synchronously.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -51,6 +52,32 @@ __global__ void __launch_bounds__(kBuildBlock)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) lbvh_refit(i, tris60, sorted_idx, pad, bt);
+}
+__global__ void __launch_bounds__(kBuildBlock)
+    k_ploc_init(uint32_t n, const float* tris60, const uint32_t* sorted_idx, float pad, BinTree bt, uint32_t* node_out,
+                float* box_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ploc_init_leaf(i, tris60, sorted_idx, pad, bt, node_out, box_out);
+}
+__global__ void __launch_bounds__(kBuildBlock) k_ploc_nn(PlocRound p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.m) ploc_nn(i, p);
+}
+__global__ void __launch_bounds__(kBuildBlock) k_ploc_flag(PlocRound p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.m) ploc_flag(i, p);
+}
+// also leaves the round's totals (survivors | merges << 32) in *total for the host
+__global__ void __launch_bounds__(kBuildBlock)
+    k_ploc_apply(PlocRound p, const unsigned long long* scan, uint32_t id_top, BinTree bt, unsigned long long* total)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    ploc_apply(i, p, scan, id_top, bt);
+    if (i == p.m - 1) *total = scan[i] + p.flag[i];
 }
 __global__ void __launch_bounds__(kBuildBlock)
     k_collapse(uint32_t n_items, const CollapseItem* items, const float* tris60, const uint32_t* sorted_idx,
@@ -173,8 +200,62 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
     bt.visits = m_visits.as<uint32_t>();
     bt.cost = m_cost.as<float>();
     bt.split = m_split.as<uint8_t>();
-    if (n_inner) k_lbvh_node<<<div_up(n_inner, kBuildBlock), kBuildBlock, 0, st>>>(n_inner, keys, bt);
-    k_lbvh_refit<<<div_up(n, kBuildBlock), kBuildBlock, 0, st>>>(n, tris60, sorted_idx, g->pad, bt);
+    const char* builder = getenv("CRT_BVH_BUILDER");
+    int ploc_rounds = 0;
+    if (builder && !strcmp(builder, "lbvh"))
+    {
+        if (n_inner) k_lbvh_node<<<div_up(n_inner, kBuildBlock), kBuildBlock, 0, st>>>(n_inner, keys, bt);
+        k_lbvh_refit<<<div_up(n, kBuildBlock), kBuildBlock, 0, st>>>(n, tris60, sorted_idx, g->pad, bt);
+    }
+    else
+    {
+        // PLOC rounds: nearest neighbour, flag, scan, apply; the host reads the survivor count after each round
+        DevMem m_na, m_nb, m_ba, m_bb, m_nn, m_flag, m_scan, m_total, m_scan_tmp;
+        CRT_ALLOC(m_na, n * sizeof(uint32_t));
+        CRT_ALLOC(m_nb, n * sizeof(uint32_t));
+        CRT_ALLOC(m_ba, (size_t)n * 8 * sizeof(float));
+        CRT_ALLOC(m_bb, (size_t)n * 8 * sizeof(float));
+        CRT_ALLOC(m_nn, n * sizeof(uint32_t));
+        CRT_ALLOC(m_flag, n * sizeof(unsigned long long));
+        CRT_ALLOC(m_scan, n * sizeof(unsigned long long));
+        CRT_ALLOC(m_total, sizeof(unsigned long long));
+        size_t scan_bytes = 0;
+        CRT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, m_flag.as<unsigned long long>(),
+                                               m_scan.as<unsigned long long>(), (int)n, st));
+        CRT_ALLOC(m_scan_tmp, scan_bytes);
+        uint32_t* node_in = m_na.as<uint32_t>();
+        uint32_t* node_out = m_nb.as<uint32_t>();
+        float* box_in = m_ba.as<float>();
+        float* box_out = m_bb.as<float>();
+        k_ploc_init<<<div_up(n, kBuildBlock), kBuildBlock, 0, st>>>(n, tris60, sorted_idx, g->pad, bt, node_in, box_in);
+        uint32_t m = n, id_top = n >= 2 ? n - 2 : 0;
+        while (m > 1)
+        {
+            PlocRound pr{m, node_in, box_in, m_nn.as<uint32_t>(), m_flag.as<unsigned long long>(), node_out, box_out};
+            const unsigned blocks = div_up(m, kBuildBlock);
+            k_ploc_nn<<<blocks, kBuildBlock, 0, st>>>(pr);
+            k_ploc_flag<<<blocks, kBuildBlock, 0, st>>>(pr);
+            CRT_CUDA(cub::DeviceScan::ExclusiveSum(m_scan_tmp.p, scan_bytes, m_flag.as<unsigned long long>(),
+                                                   m_scan.as<unsigned long long>(), (int)m, st));
+            k_ploc_apply<<<blocks, kBuildBlock, 0, st>>>(pr, m_scan.as<unsigned long long>(), id_top, bt,
+                                                        m_total.as<unsigned long long>());
+            unsigned long long total = 0;
+            CRT_CUDA(cudaMemcpyAsync(&total, m_total.p, sizeof total, cudaMemcpyDeviceToHost, st));
+            CRT_CUDA(cudaStreamSynchronize(st));
+            const uint32_t merges = (uint32_t)(total >> 32), survivors = (uint32_t)(total & 0xffffffffull);
+            if (merges == 0 || survivors >= m)
+            {
+                set_error("PLOC round made no progress (%u clusters)", m);
+                return CRT_ECUDA;
+            }
+            id_top -= merges;
+            m = survivors;
+            uint32_t* tn = node_in; node_in = node_out; node_out = tn;
+            float* tb = box_in; box_in = box_out; box_out = tb;
+            ++ploc_rounds;
+        }
+        ctx->launches += 1 + 4 * (unsigned long long)ploc_rounds;
+    }
 
     // ---- 5: collapse, one launch per level of the wide tree
     DevMem m_nodes, m_q0, m_q1, m_counters;

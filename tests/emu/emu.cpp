@@ -109,8 +109,40 @@ EmuGeom* build(const float* tris60, uint32_t n)
     std::vector<uint8_t> split((2 * (size_t)n - 1) * 8);
     BinTree bt{n, left.data(), right.data(), parent.data(), first.data(), count.data(), box.data(), visits.data(),
                cost.data(), split.data()};
-    for (uint32_t i = 0; i < ni; i++) lbvh_node(i, skeys.data(), bt);
-    for (uint32_t i = 0; i < n; i++) lbvh_refit(i, tris60, idx.data(), g->pad, bt);
+    const char* builder = getenv("CRT_BVH_BUILDER");
+    if (builder && !strcmp(builder, "lbvh"))
+    {
+        for (uint32_t i = 0; i < ni; i++) lbvh_node(i, skeys.data(), bt);
+        for (uint32_t i = 0; i < n; i++) lbvh_refit(i, tris60, idx.data(), g->pad, bt);
+    }
+    else
+    {
+        // same round structure as csrc/geometry.cu:build_ploc()
+        std::vector<uint32_t> node_a(n), node_b(n), nn(n);
+        std::vector<float> box_a((size_t)n * 8), box_b((size_t)n * 8);
+        std::vector<unsigned long long> flag(n), scan(n);
+        for (uint32_t j = 0; j < n; j++) ploc_init_leaf(j, tris60, idx.data(), g->pad, bt, node_a.data(), box_a.data());
+        uint32_t m = n, id_top = n >= 2 ? n - 2 : 0;
+        uint32_t *ni_ = node_a.data(), *no_ = node_b.data();
+        float *bi_ = box_a.data(), *bo_ = box_b.data();
+        while (m > 1)
+        {
+            PlocRound pr{m, ni_, bi_, nn.data(), flag.data(), no_, bo_};
+            for (uint32_t i = 0; i < m; i++) ploc_nn(i, pr);
+            for (uint32_t i = 0; i < m; i++) ploc_flag(i, pr);
+            unsigned long long acc = 0;
+            for (uint32_t i = 0; i < m; i++)
+            {
+                scan[i] = acc;
+                acc += flag[i];
+            }
+            for (uint32_t i = 0; i < m; i++) ploc_apply(i, pr, scan.data(), id_top, bt);
+            id_top -= (uint32_t)(acc >> 32);
+            m = (uint32_t)(acc & 0xffffffffull);
+            std::swap(ni_, no_);
+            std::swap(bi_, bo_);
+        }
+    }
 
     g->nodes.resize((size_t)n + 1);
     g->tris.resize(n);
