@@ -32,12 +32,6 @@ sys.path.insert(0, os.path.join(ROOT, "cedec-2024-rt_b200", "python"))
 
 W4K, H4K = 3840, 2160
 CAM = ((-0.579885, 22.194597, -6.567105), (5.224952, 20.847435, 1.431192))  # 10_restir_di.cpp:188-189
-HALO = 87  # |neighbour offset| <= 86.4 px (sample_2d_gaussian)
-# algorithmic bytes per pixel and kernel (reference struct sizes: Visibility 16,
-# Reservoir 76, float4 16, RGBA8 4; scene/BVH gathers and neighbour re-reads excluded)
-ALGO_BYTES = {"raycast": 16, "generate_candidate": 92, "temporal_resampling": 244, "save_temporal_reservoir": 152,
-              "spatial_resampling": 168, "resolve": 124, "tone_mapping": 20}
-RESERVOIR_PASSES = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampling", "resolve")
 
 
 def measured_peaks():
@@ -56,6 +50,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t0 = self.t1 = None  # timed region (time.time()); samples outside it are dropped when enough lie inside
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -68,13 +69,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t))]
+        where = "timed regions"
+        if len(rows) < 2:  # nvidia-smi's sampling period can exceed a short timed region: fall back to the whole run
+            rows, where = [r for _, r in self.rows], "whole run (warm-up included)"
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -86,7 +91,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": where}
 
 
 def load_workload():
@@ -101,29 +106,46 @@ def load_workload():
     return tris, ((0.0, 22.0, 0.0), (30.0, 18.0, 30.0)), "10_restir_di: PROCEDURAL stand-in scene (blocks_restir cache not staged)"
 
 
-def slab_rows(H, world, rank):
-    """row slabs of yi, balanced to multiples of 8 rows (the kernels' tile height)"""
-    edges = [((H * r // world) + 7) // 8 * 8 for r in range(world)] + [H]
-    edges[0] = 0
-    return edges[rank], edges[rank + 1]
+# compulsory HBM bytes per pixel of each kernel: (diffuse pixel, sky/emissive pixel).  Per-kernel path: the
+# reference struct sizes of SURVEY.md section 8d.  Fused path: what the fused kernels themselves have to move
+# (SoA reservoir 72 B, G-buffer 24 B, class 1 B, queue record 64 B) — smaller than the reference-equivalent
+# figure, and the one `achieved` is computed from.
+KERNEL_BYTES = {
+    "raycast": (16, 16), "generate_candidate": (92, 92), "temporal_resampling": (244, 16),
+    "save_temporal_reservoir": (152, 152), "spatial_resampling": (168, 16), "resolve": (124, 32), "tone_mapping": (20, 20),
+    "candidate_temporal": (16 + 72 + 72 + 24 + 1, 16 + 72 + 1), "spatial_fast": (1 + 24 + 72 + 72, 1),
+    "resolve_fast": (16 + 1 + 24 + 48 + 64, 16 + 1 + 16),
+    "trace_visibility_reuse": (None, None), "trace_resolve": (None, None),  # traversal: per-ray figures below
+}
+HBM_BOUND = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampling", "tone_mapping", "spatial_fast",
+             "candidate_temporal", "resolve_fast")
 
 
-# ============================================================================================== CUDA arm
+class CudaArrayView:
+    """device memory owned by libcedecrt as a torch tensor (zero-copy, __cuda_array_interface__)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
 class SlabRenderer:
     """The frame loop over one GPU's row slab.  Buffers are full-size (pixel indices stay global) and are torch
     tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
 
-    def __init__(self, torch, dist, rank, world, tris, cam, W, H):
+    def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True):
         import numpy as np
 
         import cedecrt
+        import slabs
 
         self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
-        self.c = cedecrt
+        self.c, self.slabs, self.fused = cedecrt, slabs, fused
         self.rt = cedecrt.Runtime(torch.cuda.current_device())
         assert torch.cuda.current_stream().cuda_stream != 0, "bench needs a non-default torch stream"
         self.rt.set_stream(torch.cuda.current_stream().cuda_stream)
-        self.y0, self.y1 = slab_rows(H, world, rank)
+        self.edges = [slabs.slab_rows(H, world, r)[0] for r in range(world)] + [H]
+        self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
+        self.plan = slabs.halo_plan(H, self.edges, rank) if world > 1 else []
         self.rt.set_row_range(self.y0, self.y1)
         self.options = cedecrt.Options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
         self.eye = tuple(float(np.float32(v)) for v in cam[0])
@@ -148,80 +170,66 @@ class SlabRenderer:
         self.t_r0, self.reservoir0 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
         self.t_r1, self.reservoir1 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
         self.t_tmp, self.temporal = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
+        self.bufs = self.rt.restir_buffers(self.pixels, self.accumulation, self.visibility, self.reservoir0,
+                                           self.reservoir1, self.temporal)
         self.host_pixels = torch.empty(4 * W * (self.y1 - self.y0), dtype=torch.uint8).pin_memory()
         self.frame_index = 0
-        self.kernel_ms = None
+        self.t_cls = None
+        self.halo_bytes = 0
 
-    # ---- halo exchange: rows [a, b) of yi are the byte range [(H-b)*W, (H-a)*W) * elem of a bottom-up buffer
     def _rows(self, t, elem, a, b):
         return t[(self.H - b) * self.W * elem:(self.H - a) * self.W * elem]
 
-    def exchange_halo(self, t, elem):
-        """send my boundary rows to the slab neighbours, receive theirs into the same global positions"""
-        if self.world == 1:
-            return 0
-        ops, dist, nbytes = [], self.dist, 0
-        for nb, mine, theirs in ((self.rank - 1, (self.y0, min(self.y0 + HALO, self.y1)), (max(self.y0 - HALO, 0), self.y0)),
-                                 (self.rank + 1, (max(self.y1 - HALO, self.y0), self.y1), (self.y1, min(self.y1 + HALO, self.H)))):
-            if nb < 0 or nb >= self.world:
-                continue
-            # the neighbour needs HALO of my rows; I need HALO of its rows (slabs are taller than HALO here)
-            ops.append(dist.P2POp(dist.isend, self._rows(t, elem, *mine), nb))
-            ops.append(dist.P2POp(dist.irecv, self._rows(t, elem, *theirs), nb))
-            nbytes += (mine[1] - mine[0]) * self.W * elem
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-        return nbytes
+    def exchange(self, t, layout):
+        if self.world > 1:
+            self.halo_bytes += self.slabs.exchange(self.dist, t, self.W, self.H, layout, self.plan)
 
-    def frame(self, timers=None):
+    def frame(self):
         rt, W, H, o, g, t, v, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.visibility, self.eye
+        S = self.slabs
         self.frame_index += 1
         f = self.frame_index
-
-        def run(name, fn, *a):
-            if timers is None:
-                fn(*a)
-            else:
-                e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
-                e0.record()
-                fn(*a)
-                e1.record()
-                timers.append((name, e0, e1))
-
-        run("raycast", rt.raycast, W, H, g, t, self.raygen, v)
-        self.exchange_halo(self.t_vis, 16)
-        run("generate_candidate", rt.generate_candidate, W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
-        run("temporal_resampling", rt.temporal_resampling, W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
-        run("save_temporal_reservoir", rt.save_temporal_reservoir, W, H, self.reservoir0, self.temporal)
+        if self.fused:
+            rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
+            if self.world > 1:
+                if self.t_cls is None:
+                    self.t_cls = self.torch.as_tensor(CudaArrayView(rt.restir_class_plane(), W * H), device="cuda")
+                self.exchange(self.t_cls, S.CLASS_PLANE)
+            for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
+                self.exchange(self.t_tmp if k == 0 else (self.t_r1 if k % 2 else self.t_r0), S.SOA_RESERVOIR)
+                rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
+            rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
+            return
+        rt.raycast(W, H, g, t, self.raygen, v)
+        self.exchange(self.t_vis, S.AOS_VISIBILITY)
+        rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
+        rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        rt.save_temporal_reservoir(W, H, self.reservoir0, self.temporal)
         bi, bo, ti = self.reservoir0, self.reservoir1, self.t_r0
         for k in range(o.spatial_resampling_passes):
             if k != 0:
                 bi, bo = bo, bi
                 ti = self.t_r1 if ti is self.t_r0 else self.t_r0
-            self.exchange_halo(ti, 76)
-            run("spatial_resampling", rt.spatial_resampling, W, H, f, k, g, t, v, eye, o, bi, bo)
-        run("resolve", rt.resolve, self.accumulation, W, H, g, t, v, eye, o, bo)
-        run("tone_mapping", rt.tone_mapping, self.pixels, self.accumulation, W, H)
+            self.exchange(ti, S.AOS_RESERVOIR)
+            rt.spatial_resampling(W, H, f, k, g, t, v, eye, o, bi, bo)
+        rt.resolve(self.accumulation, W, H, g, t, v, eye, o, bo)
+        rt.tone_mapping(self.pixels, self.accumulation, W, H)
 
     def download_pixels(self):
         src = self._rows(self.t_pix, 4, self.y0, self.y1)
         self.host_pixels.copy_(src, non_blocking=True)
 
 
-def rays_per_frame(torch, r):
-    """rays actually traced in one frame of config 5: 1 primary per pixel + 2 shadow rays
-    (visibility reuse, resolve) per pixel whose primary hit is a non-emissive surface; counted from the
-    visibility buffer of this rank's slab."""
-    import numpy as np
-
+def pixel_classes(torch, r):
+    """(pixels, diffuse pixels) of this rank's slab, from the visibility buffer: a diffuse pixel is one whose
+    primary hit is a non-emissive surface — the only pixels with reservoir work and shadow rays."""
     vis = r._rows(r.t_vis, 16, r.y0, r.y1).view(torch.int32).reshape(-1, 4)[:, 2]
     em = r.t_tris.view(torch.float32).reshape(-1, 15)[:, 12:15]
     is_em = (em > 0).any(1)
     hit = vis >= 0
     diffuse = hit.clone()
     diffuse[hit] = ~is_em[vis[hit].long()]
-    n_px = r.W * (r.y1 - r.y0)
-    return n_px + 2 * int(diffuse.sum().item())
+    return r.W * (r.y1 - r.y0), int(diffuse.sum().item())
 
 
 def run_cuda(args):
@@ -243,7 +251,8 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tris, cam, workload = load_workload()
     W, H = args.width, args.height
-    r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H)
+    fused = args.mode == "fused"
+    r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused)
     stats = r.geom.stats()
 
     def barrier():
@@ -251,13 +260,14 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         r.frame()
     barrier()
     launches0 = r.rt.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     # ---- timed: K frames, resident buffers
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -279,16 +289,21 @@ def run_cuda(args):
     t_e1.record()
     barrier()
     ms_e2e = t_e0.elapsed_time(t_e1)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    # ---- per-kernel device times (instrumented frames, outside the timed regions)
-    timers = []
-    for _ in range(max(2, min(args.steps, 4))):
-        r.frame(timers)
-    torch.cuda.synchronize()
+    # ---- per-kernel device times: an event after every launch (crt_profile_begin/end), steady-state frames
+    n_prof = max(2, min(args.steps, 4))
+    r.halo_bytes = 0
+    r.rt.profile_begin()
+    for _ in range(n_prof):
+        r.frame()
+    marks = r.rt.profile_end()
+    halo_bytes_per_frame = r.halo_bytes // n_prof
     per_kernel = {}
-    for name, a, b in timers:
-        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
-    rays = rays_per_frame(torch, r)
+    for name, t_ms in marks:
+        per_kernel.setdefault(name, []).append(t_ms)
+    n_px, n_diffuse = pixel_classes(torch, r)
+    rays = n_px + 2 * n_diffuse  # config 5: 1 primary per pixel + visibility-reuse + resolve ray per diffuse pixel
 
     t = torch.tensor([ms, ms_e2e, float(rays)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -298,43 +313,60 @@ def run_cuda(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, ms_e2e, rays = tmax[0].item(), tmax[1].item(), tsum[2].item()
     if rank == 0:
-        n_px = W * H
+        n_img = W * H
         peak, peak_src = measured_peaks()
-        my_px = W * (r.y1 - r.y0)
         kern = {}
         for name, ts in per_kernel.items():
             per_launch = sum(ts) / len(ts)
-            kern[name] = {"ms_per_launch": round(per_launch, 4), "launches_per_frame": len(ts) // max(2, min(args.steps, 4)),
-                          "algo_bytes_per_px": ALGO_BYTES[name],
-                          "algo_gbs": round(ALGO_BYTES[name] * my_px / per_launch / 1e6, 1)}
+            bd, bs = KERNEL_BYTES.get(name, (None, None))
+            k = {"ms_per_launch": round(per_launch, 4), "launches_per_frame": round(len(ts) / n_prof, 2)}
+            if bd is not None:
+                nbytes = bd * n_diffuse + bs * (n_px - n_diffuse)
+                k["algo_bytes_per_launch"] = int(nbytes)
+                k["algo_gbs"] = round(nbytes / per_launch / 1e6, 1)
+            elif name == "trace_resolve":
+                k["algo_bytes_per_launch"] = 96 * n_diffuse  # R 64 B record, RMW float4 accumulation
+                k["algo_gbs"] = round(96 * n_diffuse / per_launch / 1e6, 1)
+                k["mrays_per_s"] = round(n_diffuse / per_launch / 1e3, 1)
+            kern[name] = k
         frame_ms_by_kernel = {k: v["ms_per_launch"] * v["launches_per_frame"] for k, v in kern.items()}
         dominant = max(frame_ms_by_kernel, key=frame_ms_by_kernel.get)
-        res_bytes = sum(ALGO_BYTES[k] * kern[k]["launches_per_frame"] for k in RESERVOIR_PASSES) * my_px
-        res_ms = sum(frame_ms_by_kernel[k] for k in RESERVOIR_PASSES)
+        passes = [k for k in kern if k in HBM_BOUND]
+        res_bytes = sum(kern[k]["algo_bytes_per_launch"] * kern[k]["launches_per_frame"] for k in passes)
+        res_ms = sum(frame_ms_by_kernel[k] for k in passes)
+        dom = kern[dominant]
         out = {
-            "metric": "ReSTIR DI 4K Mpix/s", "value": round(n_px * args.steps / ms / 1e3, 3), "unit": "Mpix/s",
+            "metric": "ReSTIR DI 4K Mpix/s", "value": round(n_img * args.steps / ms / 1e3, 3), "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "width": W, "height": H, "triangles": r.n_tris, "lights": r.n_lights,
                        "options": "temporal+spatial(5 nbrs, r=30, 3 passes)+visibility reuse, accumulate, ris 32",
-                       "camera": "10_restir_di.cpp:188-189", "partition": "%d row slab(s), halo %d rows" % (world, HALO),
-                       "l2": "per-frame working set (3 x 630 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
+                       "camera": "10_restir_di.cpp:188-189",
+                       "mode": "fused frame (crt_restir_frame_begin / spatial_pass / frame_end, SoA reservoirs)" if fused
+                               else "per-kernel launch list (drop-in, AoS reservoirs)",
+                       "partition": "%d row slab(s), halo %d rows, %d halo bytes sent per frame by rank 0" % (
+                           world, r.slabs.HALO, halo_bytes_per_frame),
+                       "l2": "per-frame working set (3 x 600 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
                        "math": "libdevice float (reference NVRTC semantics), -fmad=false"},
             "grays_per_s": round(rays * args.steps / ms / 1e6, 4), "rays_per_frame": int(rays),
-            "e2e": {"value": round(n_px * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s",
-                    "h2d_bytes_per_step": 96, "d2h_bytes_per_step": 4 * n_px,
+            "e2e": {"value": round(n_img * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s",
+                    "h2d_bytes_per_step": 96, "d2h_bytes_per_step": 4 * n_img,
                     "note": "per-frame inputs (RayGenerator 36 B, eye 12 B, Options 48 B) go as kernel parameters; "
                             "the RGBA8 frame is copied to pinned host memory every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dominant, "bound": "hbm",
-                         "achieved": kern[dominant]["algo_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": round(kern[dominant]["algo_gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
-                         "note": "dominant kernel by time; traversal kernels are latency/cache-bound, see profiles/"},
+                         "achieved": dom.get("algo_gbs"), "peak": peak, "unit": "GB/s",
+                         "frac": round(dom["algo_gbs"] / peak, 4) if dom.get("algo_gbs") else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "dominant kernel by time. Traversal kernels (raycast, trace_*) are SM-issue-bound, not "
+                                 "HBM-bound: see profiles/ for issue utilisation and L1/L2 hit rates; the HBM-bound "
+                                 "kernels are summarised in roofline_reservoir_passes"},
             "roofline_reservoir_passes": {"bound": "hbm", "achieved": round(res_bytes / res_ms / 1e6, 1), "peak": peak,
                                           "unit": "GB/s", "frac": round(res_bytes / res_ms / 1e6 / peak, 4),
-                                          "kernels": list(RESERVOIR_PASSES)},
+                                          "kernels": passes, "ms_per_frame": round(res_ms, 4)},
             "kernels": kern,
+            "pixels": {"slab": n_px, "diffuse": n_diffuse},
             "bvh": {k: stats[k] for k in ("n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes")},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -461,6 +493,8 @@ def main():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--cpu-rows", type=int, default=64, help="band height of the CPU arm's per-step sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fused", choices=["fused", "dropin"],
+                    help="fused: one crt_restir_* frame call sequence (default); dropin: the reference's launch list")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -62,6 +62,10 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
     cudaEventDestroy(ctx->ev_stop);
     if (ctx->queue_rays) cudaFree(ctx->queue_rays);
     if (ctx->queue_counters) cudaFree(ctx->queue_counters);
+    if (ctx->gbuf) cudaFree(ctx->gbuf);
+    for (auto& m : ctx->prof_marks) cudaEventDestroy(m.second);
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return CRT_OK;
@@ -154,6 +158,47 @@ extern "C" int crt_timer_stop_ms(crt_ctx* ctx, float* ms)
     CRT_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
     CRT_CUDA(cudaEventSynchronize(ctx->ev_stop));
     CRT_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+    return CRT_OK;
+}
+
+// ---- per-kernel device times.  Between begin and end every kernel launch of this context is followed by an
+// event on the context's stream; end() synchronises and reports, per launch, the time since the previous event
+// (kernels of one stream run back to back, so that is the kernel's duration plus any memset/copy queued before it).
+extern "C" int crt_profile_begin(crt_ctx* ctx)
+{
+    CRT_REQUIRE(ctx, "null context");
+    if (!ctx->prof_start) CRT_CUDA(cudaEventCreate(&ctx->prof_start));
+    for (auto& m : ctx->prof_marks) ctx->prof_pool.push_back(m.second);
+    ctx->prof_marks.clear();
+    CRT_CUDA(cudaEventRecord(ctx->prof_start, ctx->stream));
+    ctx->profiling = true;
+    return CRT_OK;
+}
+extern "C" int crt_profile_end(crt_ctx* ctx, char* names, size_t names_cap, float* ms, int ms_cap, int* count)
+{
+    CRT_REQUIRE(ctx && names && ms && count, "null argument");
+    CRT_REQUIRE(ctx->profiling, "crt_profile_begin was not called");
+    ctx->profiling = false;
+    CRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    size_t used = 0;
+    int n = 0;
+    cudaEvent_t prev = ctx->prof_start;
+    if (names_cap) names[0] = 0;
+    for (auto& m : ctx->prof_marks)
+    {
+        const size_t len = strlen(m.first);
+        if (n >= ms_cap || used + len + 2 > names_cap) break;
+        CRT_CUDA(cudaEventElapsedTime(&ms[n], prev, m.second));
+        memcpy(names + used, m.first, len);
+        used += len;
+        names[used++] = '\n';
+        names[used] = 0;
+        prev = m.second;
+        n++;
+    }
+    *count = n;
+    for (auto& m : ctx->prof_marks) ctx->prof_pool.push_back(m.second);
+    ctx->prof_marks.clear();
     return CRT_OK;
 }
 

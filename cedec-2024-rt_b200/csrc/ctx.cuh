@@ -4,6 +4,8 @@
 #include <stdio.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/cedecrt.h"
 #include "bvh.cuh"
@@ -23,8 +25,16 @@ struct crt_ctx
     size_t queue_capacity = 0;
     int wavefront = 1;  // 0: trace shadow rays inside the per-pixel kernels (CRT_WAVEFRONT=0)
     int light_table = 1;  // 0: sample lights through lights[] -> triangles[] like the reference (CRT_LIGHT_TABLE=0)
+    // fused frame (kernels_fast.cu): G-buffer + pixel-class plane, 25 bytes per pixel, grown on demand
+    void* gbuf = nullptr;
+    size_t gbuf_pixels = 0;
     int row_begin = 0, row_end = -1;  // rows of yi this context computes (crt_set_row_range); -1 = image height
     unsigned long long launches = 0;  // kernels launched through this context (bench.py: gpu_launches)
+    // crt_profile_begin/end: an event after every launch; consecutive differences are per-kernel device times
+    bool profiling = false;
+    cudaEvent_t prof_start = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 struct crt_geometry_t
@@ -73,6 +83,18 @@ void set_error(const char* fmt, ...);
 inline int check_launch(crt_ctx* ctx, const char* what)
 {
     ctx->launches++;
+    if (ctx->profiling)
+    {
+        cudaEvent_t ev = nullptr;
+        if (!ctx->prof_pool.empty())
+        {
+            ev = ctx->prof_pool.back();
+            ctx->prof_pool.pop_back();
+        }
+        else cudaEventCreate(&ev);
+        cudaEventRecord(ev, ctx->stream);
+        ctx->prof_marks.emplace_back(what, ev);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
     {

@@ -7,83 +7,43 @@
 // tile and each warp an 8x4 sub-tile (the reference's linear tid gives 32x1 strips): primary rays of a
 // warp stay coherent and the Gaussian neighbourhoods of a block overlap in L1.  Randomness is keyed on
 // (xi, yi, frame, stage), so the mapping does not change any result.
-#include "ctx.cuh"
-#include "shadow_queue.cuh"
+#include "launch_common.cuh"
 
 namespace crt
 {
-constexpr int kTileW = 32, kTileH = 8;
-
-// pixel of this thread
-struct TilePix
-{
-    Pix px;
-    bool in;
-};
-// rows [y0, y1) of the image are processed (multi-GPU row slabs: crt_set_row_range); pixel coordinates stay global
-struct Rows
-{
-    int y0, y1;
-};
-__device__ __forceinline__ TilePix this_pixel(int W, int H, Rows rows)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xi = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
-    const int yi = rows.y0 + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
-    return {make_pix(xi, yi, W, H), xi < W && yi < rows.y1};
-}
-static dim3 tile_grid(int W, Rows r)
-{
-    const int ny = (r.y1 - r.y0 + kTileH - 1) / kTileH;
-    return dim3((W + kTileW - 1) / kTileW, ny > 0 ? ny : 1);  // an empty slab still launches one (idle) row of tiles
-}
-static Rows rows_of(const crt_ctx* ctx, int H)
-{
-    Rows r{ctx->row_begin, ctx->row_end < 0 || ctx->row_end > H ? H : ctx->row_end};
-    if (r.y0 < 0) r.y0 = 0;
-    if (r.y0 > r.y1) r.y0 = r.y1;
-    return r;
-}
-
 __global__ void __launch_bounds__(256) k_raycast(int W, int H, Rows rows, Bvh bvh, crt_raygen raygen, crt_visibility* vis)
 {
     const TilePix t = this_pixel(W, H, rows);
     if (t.in) px_raycast(t.px, W, H, bvh, raygen, vis);
 }
-__device__ __forceinline__ ShadowRay to_shadow_ray(const DeferredRay& d, int pix)
-{
-    ShadowRay r;
-    r.ox = d.org.x; r.oy = d.org.y; r.oz = d.org.z;
-    r.pix = (uint32_t)pix;
-    r.dx = d.dir.x; r.dy = d.dir.y; r.dz = d.dir.z;
-    r.ucw = 0.0f;
-    r.bgx = r.bgy = r.bgz = r.pad0 = r.rx = r.ry = r.rz = r.pad1 = 0.0f;
-    return r;
-}
 // WF: emit the visibility-reuse ray into the queue instead of walking it here (shadow_queue.cuh)
-template <class L, bool WF>
+// SH: use_shadowed_target_function may be set (traversal code inside the target function); the common SH = false
+// instantiation has none, which takes the walk's stack and ~40 registers out of the reservoir kernels
+template <bool SH>
+__device__ __forceinline__ Opt kernel_opt(const crt_options& options)
+{
+    Opt o = make_opt(options);
+    if (!SH) o.shadowed = false;
+    return o;
+}
+template <class L, bool WF, bool SH>
 __global__ void __launch_bounds__(256)
     k_generate_candidate(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
                          L lights, crt_options options, crt_reservoir* out, ShadowQueue q)
 {
     const TilePix t = this_pixel(W, H, rows);
     DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
-    if (t.in) d = px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, make_opt(options), AosStore{out}, WF);
+    if (t.in) d = px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, kernel_opt<SH>(options), AosStore{out}, WF);
     if (WF) queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
 }
-__global__ void __launch_bounds__(256) k_build_light_table(uint32_t n, const float* tris60, const uint32_t* lights, LightRec* table)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) table[i] = make_light_rec(tris60, lights[i]);
-}
-template <int MODE>
+template <int MODE, bool SH>
 __global__ void __launch_bounds__(256)
     k_temporal(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
                crt_options options, const crt_reservoir* prev, crt_reservoir* cur)
 {
     const TilePix t = this_pixel(W, H, rows);
     if (t.in)
-        px_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, make_opt(options),
+        px_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, kernel_opt<SH>(options),
                                 AosStore{const_cast<crt_reservoir*>(prev)}, AosStore{cur});
 }
 // 10_restir_di.cu:239-254 (the first buffer is the source).  Every pixel is copied, so the bottom-up
@@ -93,14 +53,14 @@ __global__ void __launch_bounds__(256) k_save_temporal(size_t n_words, const uin
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = src[i];
 }
-template <int MODE>
+template <int MODE, bool SH>
 __global__ void __launch_bounds__(256)
     k_spatial(int W, int H, Rows rows, int frame, int pass, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
               crt_options options, const crt_reservoir* in, crt_reservoir* out)
 {
     const TilePix t = this_pixel(W, H, rows);
     if (t.in)
-        px_spatial<Math<MODE>>(t.px, W, H, frame, pass, bvh, tris60, vis, eye, make_opt(options),
+        px_spatial<Math<MODE>>(t.px, W, H, frame, pass, bvh, tris60, vis, eye, kernel_opt<SH>(options),
                                AosStore{const_cast<crt_reservoir*>(in)}, AosStore{out});
 }
 template <bool WF>
@@ -160,73 +120,6 @@ __global__ void __launch_bounds__(256)
 // ======================================================================================= C ABI
 using namespace crt;
 
-namespace
-{
-inline size_t bsize(const crt_buffer& b) { return (size_t)CRT_BUFFER_SIZE(b); }
-inline f3 to_f3(const crt_float3& v) { return f3{v.x, v.y, v.z}; }
-inline unsigned sweep_blocks(crt_ctx* ctx, size_t n)
-{
-    const size_t want = (n + 255) / 256, cap = (size_t)ctx->sm_count * 8;
-    return (unsigned)(want < cap ? (want ? want : 1) : cap);
-}
-}  // namespace
-
-// ---- wavefront plumbing
-static int queue_prepare(crt_ctx* ctx, size_t n_pixels, ShadowQueue* q)
-{
-    if (ctx->queue_capacity < n_pixels)
-    {
-        if (ctx->queue_rays) CRT_CUDA(cudaFree(ctx->queue_rays));
-        ctx->queue_rays = nullptr;
-        ctx->queue_capacity = 0;
-        CRT_CUDA(cudaMalloc(&ctx->queue_rays, n_pixels * sizeof(ShadowRay)));
-        ctx->queue_capacity = n_pixels;
-    }
-    if (!ctx->queue_counters) CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 2 * sizeof(unsigned)));
-    CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 2 * sizeof(unsigned), ctx->stream));
-    q->rays = (ShadowRay*)ctx->queue_rays;
-    q->count = ctx->queue_counters;
-    q->next = ctx->queue_counters + 1;
-    q->capacity = (uint32_t)ctx->queue_capacity;
-    return CRT_OK;
-}
-template <int EPI>
-static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, const ShadowSink& sink)
-{
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm)
-    {
-        CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_shadow_queue<EPI>, kShadowWarps * 32, 0));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
-    k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, ctx->stream>>>(geom->view(), q, sink);
-    return check_launch(ctx, "trace_shadow_queue");
-}
-// light records for (geometry, light list); rebuilt when another list is passed
-static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60, const uint32_t* lights, size_t n,
-                           const LightRec** out)
-{
-    if (geom->light_table_key != lights || geom->light_table_n != n)
-    {
-        if (geom->light_table) CRT_CUDA(cudaFree(geom->light_table));
-        geom->light_table = nullptr;
-        CRT_CUDA(cudaMalloc(&geom->light_table, (n ? n : 1) * sizeof(LightRec)));
-        if (n)
-        {
-            k_build_light_table<<<div_up(n, 256), 256, 0, ctx->stream>>>((uint32_t)n, tris60, lights, (LightRec*)geom->light_table);
-            const int rc = check_launch(ctx, "build_light_table");
-            if (rc != CRT_OK) return rc;
-        }
-        geom->light_table_key = lights;
-        geom->light_table_n = n;
-    }
-    *out = (const LightRec*)geom->light_table;
-    return CRT_OK;
-}
-
-#define CRT_CHECK_IMAGE(W, H) CRT_REQUIRE((W) > 0 && (H) > 0 && (size_t)(W) * (size_t)(H) < 0x7fffffffull, "bad image size")
-#define CRT_CHECK_BUF(b, n, what) CRT_REQUIRE((b).data != nullptr && bsize(b) >= (size_t)(n), what " buffer too small or null")
-
 extern "C" int crt_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_raygen raygen,
                            crt_buffer visibility_buffer)
 {
@@ -263,24 +156,25 @@ extern "C" int crt_generate_candidate(crt_ctx* ctx, int W, int H, int frame, crt
         if (rc != CRT_OK) return rc;
     }
     const dim3 grid = tile_grid(W, rows);
+    const bool sh = options.use_shadowed_target_function != 0;
     if (ctx->light_table)
     {
         const LightRec* table = nullptr;
         const int rc = light_table_for(ctx, geom, tris60, (const uint32_t*)lights.data, n_lights, &table);
         if (rc != CRT_OK) return rc;
         const LightsTable L{table, n_lights};
-        if (wf) k_generate_candidate<LightsTable, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
-        else k_generate_candidate<LightsTable, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
+        if (wf) { if (sh) k_generate_candidate<LightsTable, true, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); else k_generate_candidate<LightsTable, true, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); }
+        else { if (sh) k_generate_candidate<LightsTable, false, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); else k_generate_candidate<LightsTable, false, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); }
     }
     else
     {
         const LightsIndexed L{tris60, (const uint32_t*)lights.data, n_lights};
-        if (wf) k_generate_candidate<LightsIndexed, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
-        else k_generate_candidate<LightsIndexed, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q);
+        if (wf) { if (sh) k_generate_candidate<LightsIndexed, true, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); else k_generate_candidate<LightsIndexed, true, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); }
+        else { if (sh) k_generate_candidate<LightsIndexed, false, true><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); else k_generate_candidate<LightsIndexed, false, false><<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, res, q); }
     }
     int rc = check_launch(ctx, "generate_candidate");
     if (rc != CRT_OK || !wf) return rc;
-    return queue_trace<kEpiReservoirVisibility>(ctx, geom, q, ShadowSink{res, nullptr, 0});
+    return queue_trace<kEpiReservoirVisibility>(ctx, geom, q, ShadowSink{res, nullptr, 0, nullptr});
 }
 
 extern "C" int crt_temporal_resampling(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
@@ -293,7 +187,8 @@ extern "C" int crt_temporal_resampling(crt_ctx* ctx, int W, int H, int frame, cr
     CRT_CHECK_BUF(previous_reservoirs, (size_t)W * H, "previous reservoir");
     CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
-    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_temporal<1> : k_temporal<0>;
+    const bool ex = ctx->math_mode == CRT_MATH_EXACT, sh = options.use_shadowed_target_function != 0;
+    auto k = ex ? (sh ? k_temporal<1, true> : k_temporal<1, false>) : (sh ? k_temporal<0, true> : k_temporal<0, false>);
     k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data,
                                                (const crt_visibility*)visibility_buffer.data, to_f3(eye), options,
                                                (const crt_reservoir*)previous_reservoirs.data,
@@ -328,7 +223,8 @@ extern "C" int crt_spatial_resampling(crt_ctx* ctx, int W, int H, int frame, int
     CRT_CHECK_BUF(reservoirs, (size_t)W * H, "output reservoir");
     CRT_REQUIRE(previous_reservoirs.data != reservoirs.data, "spatial_resampling cannot run in place");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
-    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_spatial<1> : k_spatial<0>;
+    const bool ex = ctx->math_mode == CRT_MATH_EXACT, sh = options.use_shadowed_target_function != 0;
+    auto k = ex ? (sh ? k_spatial<1, true> : k_spatial<1, false>) : (sh ? k_spatial<0, true> : k_spatial<0, false>);
     k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, pass, geom->view(), (const float*)triangles.data,
                                                (const crt_visibility*)visibility_buffer.data, to_f3(eye), options,
                                                (const crt_reservoir*)previous_reservoirs.data,
@@ -358,7 +254,7 @@ extern "C" int crt_resolve(crt_ctx* ctx, crt_buffer accumulation, int W, int H, 
                                                                     options, (const crt_reservoir*)reservoirs.data, q);
         rc = check_launch(ctx, "resolve");
         if (rc != CRT_OK) return rc;
-        return queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate});
+        return queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr});
     }
     k_resolve<false><<<tile_grid(W, rows), 256, 0, ctx->stream>>>(accum, W, H, rows, geom->view(), (const float*)triangles.data,
                                                                  (const crt_visibility*)visibility_buffer.data, to_f3(eye),

@@ -1,0 +1,283 @@
+// kernels_fast.cu — the fused ReSTIR DI frame ("fast mode"): crt_restir_di_frame and its staged form.
+//
+// One call replaces the launch list of examples/10_restir_di/10_restir_di.cpp:270-372.  The per-pixel bodies are
+// in restir_fast.cuh (what is fused and why); this file holds the kernels and the frame schedule:
+//
+//   k_raycast                    primary visibility                         (10_restir_di.cu:9-34)
+//   k_candidate_temporal         RIS candidates + temporal merge, in place  (:36-237, save_temporal :239-254 vanishes)
+//   k_trace_shadow_queue<2>      visibility-reuse rays of surviving candidates only
+//   k_spatial_fast  x passes     temporal -> reservoir1 -> reservoir0 -> reservoir1 ...   (:256-388)
+//   k_resolve_fast               sky/emissive pixels finished, shading factors + ray queued (:390-459)
+//   k_trace_shadow_queue<1>      resolve rays; accumulation written in the epilogue
+//   k_tone_mapping               (crt_tone_mapping, common.cu:30-74)
+//
+// Buffer roles (all planar SoA, restir_fast.cuh: SoaStore, inside the caller's TypedBuffer<Reservoir> storage):
+// `temporal` is read (last frame) and rewritten (this frame) in place; spatial pass 0 reads it and writes
+// reservoir1, later passes ping-pong reservoir1 <-> reservoir0, so the final reservoirs are where the reference
+// leaves them (reservoir1 for an odd pass count, reservoir0 for an even one).
+//
+// Options the fused bodies do not cover (use_shadowed_target_function: rays inside the target function) run the
+// per-kernel path of kernels_dropin.cu on AoS buffers instead — same results, reference data flow.
+#include "launch_common.cuh"
+
+namespace crt
+{
+template <class L, int MODE>
+__global__ void __launch_bounds__(256)
+    k_candidate_temporal(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+                         L lights, crt_options options, SoaStore temporal, GBuf g, ShadowQueue q)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
+    if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, lights, make_opt(options), temporal, g);
+    queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
+}
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    k_spatial_fast(int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye, crt_options options, SoaStore in,
+                   SoaStore out, GBuf g)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    if (t.in) px_spatial_fast<Math<MODE>>(t.px, W, H, frame, pass, bvh, eye, make_opt(options), in, out, g);
+}
+__global__ void __launch_bounds__(256)
+    k_resolve_fast(crt_float4* accum, int W, int H, Rows rows, const float* tris60,
+                   const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
+    DeferredShade sh{{0, 0, 0}, {0, 0, 0}, 0.0f};
+    if (t.in) d = px_resolve_fast(t.px, accum, tris60, vis, res, g, sh);
+    ShadowRay r = to_shadow_ray(d, t.px.idx);
+    r.ucw = sh.ucw;
+    r.bgx = sh.bg.x; r.bgy = sh.bg.y; r.bgz = sh.bg.z;
+    r.rx = sh.rad.x; r.ry = sh.rad.y; r.rz = sh.rad.z;
+    queue_push(q, d.want, r);
+}
+// layout conversion for inspection / parity dumps / switching modes with history
+__global__ void __launch_bounds__(256) k_soa_to_aos(size_t n, SoaStore s, crt_reservoir* aos)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) soa_to_aos(s, aos, (int)i);
+}
+__global__ void __launch_bounds__(256) k_aos_to_soa(size_t n, const crt_reservoir* aos, SoaStore s)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) aos_to_soa(aos, s, (int)i);
+}
+}  // namespace crt
+
+using namespace crt;
+
+namespace
+{
+int ensure_gbuf(crt_ctx* ctx, size_t n, GBuf* g)
+{
+    if (ctx->gbuf_pixels < n)
+    {
+        if (ctx->gbuf) CRT_CUDA(cudaFree(ctx->gbuf));
+        ctx->gbuf = nullptr;
+        ctx->gbuf_pixels = 0;
+        CRT_CUDA(cudaMalloc(&ctx->gbuf, n * 25 + 256));
+        CRT_CUDA(cudaMemsetAsync(ctx->gbuf, 0, n * 25 + 256, ctx->stream));
+        ctx->gbuf_pixels = n;
+    }
+    const size_t cap = ctx->gbuf_pixels;
+    g->g0 = (char*)ctx->gbuf;
+    g->g1 = g->g0 + cap * 16;
+    g->cls = (uint8_t*)(g->g1 + cap * 8);
+    return CRT_OK;
+}
+bool fused(const crt_options& o) { return !o.use_shadowed_target_function; }
+SoaStore soa(const crt_buffer& b, size_t n) { return SoaStore{(char*)b.data, n}; }
+int check_buffers(int W, int H, const crt_restir_buffers* b)
+{
+    CRT_REQUIRE(b, "null buffer set");
+    CRT_CHECK_IMAGE(W, H);
+    const size_t n = (size_t)W * H;
+    CRT_CHECK_BUF(b->pixels, n * 4, "pixel");
+    CRT_CHECK_BUF(b->accumulation, n, "accumulation");
+    CRT_CHECK_BUF(b->visibility, n, "visibility");
+    CRT_CHECK_BUF(b->reservoir0, n, "reservoir0");
+    CRT_CHECK_BUF(b->reservoir1, n, "reservoir1");
+    CRT_CHECK_BUF(b->temporal, n, "temporal reservoir");
+    CRT_REQUIRE(b->reservoir0.data != b->reservoir1.data && b->reservoir0.data != b->temporal.data &&
+                    b->reservoir1.data != b->temporal.data,
+                "the three reservoir buffers must be distinct");
+    return CRT_OK;
+}
+// input and output of spatial pass k in fused mode
+void pass_buffers(const crt_restir_buffers* b, int pass, crt_buffer* in, crt_buffer* out)
+{
+    if (pass == 0) { *in = b->temporal; *out = b->reservoir1; }
+    else if (pass % 2) { *in = b->reservoir1; *out = b->reservoir0; }
+    else { *in = b->reservoir0; *out = b->reservoir1; }
+}
+}  // namespace
+
+extern "C" int crt_restir_output_buffer(crt_options options, const crt_restir_buffers* b, crt_buffer* out)
+{
+    CRT_REQUIRE(b && out, "null argument");
+    const int passes = options.spatial_resampling_passes;
+    if (fused(options) && (!options.use_spatial_resampling || passes <= 0)) *out = b->temporal;
+    else *out = (passes % 2) ? b->reservoir1 : b->reservoir0;  // the reference's buf_output (10_restir_di.cpp:324-336)
+    return CRT_OK;
+}
+
+extern "C" int crt_restir_is_fused(crt_options options) { return fused(options) ? 1 : 0; }
+
+extern "C" int crt_restir_class_plane(crt_ctx* ctx, void** out)
+{
+    CRT_REQUIRE(ctx && out, "null argument");
+    CRT_REQUIRE(ctx->gbuf, "no fused frame has run on this context yet");
+    *out = (char*)ctx->gbuf + ctx->gbuf_pixels * 24;
+    return CRT_OK;
+}
+
+extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                      crt_raygen raygen, crt_float3 eye, crt_buffer lights, crt_options options,
+                                      const crt_restir_buffers* b)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    int rc = check_buffers(W, H, b);
+    if (rc != CRT_OK) return rc;
+    rc = crt_raycast(ctx, W, H, geom, triangles, raygen, b->visibility);
+    if (rc != CRT_OK) return rc;
+    if (!fused(options))
+    {
+        rc = crt_generate_candidate(ctx, W, H, frame, geom, triangles, b->visibility, eye, lights, options, b->reservoir0);
+        if (rc == CRT_OK) rc = crt_temporal_resampling(ctx, W, H, frame, geom, triangles, b->visibility, eye, options, b->temporal, b->reservoir0);
+        if (rc == CRT_OK) rc = crt_save_temporal_reservoir(ctx, W, H, b->reservoir0, b->temporal);
+        return rc;
+    }
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    CRT_REQUIRE(bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
+    CRT_REQUIRE(bsize(lights) < 0xffffffffull, "too many lights");
+    const size_t n = (size_t)W * H;
+    const Rows rows = rows_of(ctx, H);
+    GBuf g;
+    rc = ensure_gbuf(ctx, n, &g);
+    if (rc != CRT_OK) return rc;
+    ShadowQueue q{nullptr, nullptr, nullptr, 0};
+    rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
+    if (rc != CRT_OK) return rc;
+    const float* tris60 = (const float*)triangles.data;
+    const crt_visibility* vis = (const crt_visibility*)b->visibility.data;
+    const uint32_t n_lights = (uint32_t)bsize(lights);
+    const SoaStore T = soa(b->temporal, n);
+    const dim3 grid = tile_grid(W, rows);
+    const bool exact = ctx->math_mode == CRT_MATH_EXACT;
+    if (ctx->light_table)
+    {
+        const LightRec* table = nullptr;
+        rc = light_table_for(ctx, geom, tris60, (const uint32_t*)lights.data, n_lights, &table);
+        if (rc != CRT_OK) return rc;
+        const LightsTable L{table, n_lights};
+        auto k = exact ? k_candidate_temporal<LightsTable, 1> : k_candidate_temporal<LightsTable, 0>;
+        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q);
+    }
+    else
+    {
+        const LightsIndexed L{tris60, (const uint32_t*)lights.data, n_lights};
+        auto k = exact ? k_candidate_temporal<LightsIndexed, 1> : k_candidate_temporal<LightsIndexed, 0>;
+        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q);
+    }
+    rc = check_launch(ctx, "candidate_temporal");
+    if (rc != CRT_OK || !options.use_visibility_reuse) return rc;
+    return queue_trace<kEpiSoaVisibility>(ctx, geom, q, ShadowSink{nullptr, nullptr, 0, (uint32_t*)T.plane(2, 0)});
+}
+
+extern "C" int crt_restir_spatial_pass(crt_ctx* ctx, int W, int H, int frame, int pass, crt_geometry geom,
+                                       crt_buffer triangles, crt_float3 eye, crt_options options,
+                                       const crt_restir_buffers* b)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    int rc = check_buffers(W, H, b);
+    if (rc != CRT_OK) return rc;
+    CRT_REQUIRE(pass >= 0, "negative pass index");
+    if (!fused(options))
+    {
+        const bool odd = pass % 2;  // the reference's swap (10_restir_di.cpp:324-336): buf0 -> buf1, buf1 -> buf0, ...
+        return crt_spatial_resampling(ctx, W, H, frame, pass, geom, triangles, b->visibility, eye, options,
+                                      odd ? b->reservoir1 : b->reservoir0, odd ? b->reservoir0 : b->reservoir1);
+    }
+    if (!options.use_spatial_resampling) return CRT_OK;  // the reference's disabled pass is a copy
+    CRT_REQUIRE(ctx->gbuf && ctx->gbuf_pixels >= (size_t)W * H, "crt_restir_frame_begin has not run for this image size");
+    const size_t n = (size_t)W * H;
+    const Rows rows = rows_of(ctx, H);
+    GBuf g;
+    rc = ensure_gbuf(ctx, n, &g);
+    if (rc != CRT_OK) return rc;
+    crt_buffer in, out;
+    pass_buffers(b, pass, &in, &out);
+    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_spatial_fast<1> : k_spatial_fast<0>;
+    k<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(W, H, rows, frame, pass, geom->view(), to_f3(eye), options, soa(in, n), soa(out, n), g);
+    return check_launch(ctx, "spatial_fast");
+}
+
+extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_float3 eye,
+                                    crt_options options, const crt_restir_buffers* b)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    int rc = check_buffers(W, H, b);
+    if (rc != CRT_OK) return rc;
+    crt_buffer fin;
+    crt_restir_output_buffer(options, b, &fin);
+    if (!fused(options))
+    {
+        rc = crt_resolve(ctx, b->accumulation, W, H, geom, triangles, b->visibility, eye, options, fin);
+        if (rc == CRT_OK) rc = crt_tone_mapping(ctx, b->pixels, b->accumulation, W, H);
+        return rc;
+    }
+    CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    CRT_REQUIRE(ctx->gbuf && ctx->gbuf_pixels >= (size_t)W * H, "crt_restir_frame_begin has not run for this image size");
+    const size_t n = (size_t)W * H;
+    const Rows rows = rows_of(ctx, H);
+    GBuf g;
+    rc = ensure_gbuf(ctx, n, &g);
+    if (rc != CRT_OK) return rc;
+    ShadowQueue q{nullptr, nullptr, nullptr, 0};
+    rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
+    if (rc != CRT_OK) return rc;
+    crt_float4* accum = (crt_float4*)b->accumulation.data;
+    k_resolve_fast<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(accum, W, H, rows, (const float*)triangles.data,
+                                                               (const crt_visibility*)b->visibility.data, soa(fin, n), g, q);
+    rc = check_launch(ctx, "resolve_fast");
+    if (rc != CRT_OK) return rc;
+    rc = queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr});
+    if (rc != CRT_OK) return rc;
+    return crt_tone_mapping(ctx, b->pixels, b->accumulation, W, H);
+}
+
+extern "C" int crt_restir_di_frame(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
+                                   crt_raygen raygen, crt_float3 eye, crt_buffer lights, crt_options options,
+                                   const crt_restir_buffers* b)
+{
+    int rc = crt_restir_frame_begin(ctx, W, H, frame, geom, triangles, raygen, eye, lights, options, b);
+    for (int pass = 0; rc == CRT_OK && pass < options.spatial_resampling_passes; pass++)
+        rc = crt_restir_spatial_pass(ctx, W, H, frame, pass, geom, triangles, eye, options, b);
+    if (rc == CRT_OK) rc = crt_restir_frame_end(ctx, W, H, geom, triangles, eye, options, b);
+    return rc;
+}
+
+extern "C" int crt_reservoir_export_aos(crt_ctx* ctx, int W, int H, crt_buffer soa_storage, crt_buffer aos_out)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_CHECK_IMAGE(W, H);
+    const size_t n = (size_t)W * H;
+    CRT_CHECK_BUF(soa_storage, n, "SoA reservoir");
+    CRT_CHECK_BUF(aos_out, n, "AoS reservoir");
+    CRT_REQUIRE(soa_storage.data != aos_out.data, "conversion cannot run in place");
+    k_soa_to_aos<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, soa(soa_storage, n), (crt_reservoir*)aos_out.data);
+    return check_launch(ctx, "soa_to_aos");
+}
+
+extern "C" int crt_reservoir_import_aos(crt_ctx* ctx, int W, int H, crt_buffer aos_in, crt_buffer soa_storage)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_CHECK_IMAGE(W, H);
+    const size_t n = (size_t)W * H;
+    CRT_CHECK_BUF(soa_storage, n, "SoA reservoir");
+    CRT_CHECK_BUF(aos_in, n, "AoS reservoir");
+    CRT_REQUIRE(soa_storage.data != aos_in.data, "conversion cannot run in place");
+    k_aos_to_soa<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (const crt_reservoir*)aos_in.data, soa(soa_storage, n));
+    return check_launch(ctx, "aos_to_soa");
+}

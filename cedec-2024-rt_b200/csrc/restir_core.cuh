@@ -101,11 +101,19 @@ struct LightsIndexed
     const float* tris60;
     const uint32_t* lights;
     uint32_t n;
-    CRT_HD LightSample sample(float rv0, float rv1, float rv2) const
+    struct Raw
+    {
+        const float* tri;
+    };
+    CRT_HD Raw fetch(float rv0) const
     {
         uint32_t nth = (uint32_t)(rv0 * (float)n);
         if (nth == n) nth = n - 1;
-        const TriRef t = tri_at(tris60, (int)CRT_LDG(lights + nth));
+        return Raw{tris60 + (size_t)CRT_LDG(lights + nth) * 15};
+    }
+    CRT_HD LightSample finish(const Raw& raw, float rv1, float rv2) const
+    {
+        const TriRef t{raw.tri};
         const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2);
         const f2 b = warp_unit_triangle(rv1, rv2);
         LightSample ls;
@@ -117,6 +125,7 @@ struct LightsIndexed
         ls.emissive = t.emissive();
         return ls;
     }
+    CRT_HD LightSample sample(float rv0, float rv1, float rv2) const { return finish(fetch(rv0), rv1, rv2); }
 };
 struct alignas(16) LightRec  // 64 bytes
 {
@@ -138,12 +147,21 @@ struct LightsTable
 {
     const LightRec* table;
     uint32_t n;
-    CRT_HD LightSample sample(float rv0, float rv1, float rv2) const
+    struct Raw
+    {
+        u4 a, b, c, d;
+    };
+    // the gather, separated from the arithmetic so that callers can have several records in flight
+    CRT_HD Raw fetch(float rv0) const
     {
         uint32_t nth = (uint32_t)(rv0 * (float)n);
         if (nth == n) nth = n - 1;
         const char* q = (const char*)(table + nth);
-        const u4 a = load_u4(q), b4 = load_u4(q + 16), c4 = load_u4(q + 32), d = load_u4(q + 48);
+        return Raw{load_u4(q), load_u4(q + 16), load_u4(q + 32), load_u4(q + 48)};
+    }
+    CRT_HD LightSample finish(const Raw& raw, float rv1, float rv2) const
+    {
+        const u4 &a = raw.a, &b4 = raw.b, &c4 = raw.c, &d = raw.d;
         const f3 v0{u2f(a.x), u2f(a.y), u2f(a.z)}, v1{u2f(b4.x), u2f(b4.y), u2f(b4.z)}, v2{u2f(c4.x), u2f(c4.y), u2f(c4.z)};
         const f2 b = warp_unit_triangle(rv1, rv2);
         LightSample ls;
@@ -153,6 +171,7 @@ struct LightsTable
         ls.emissive = f3{u2f(d.x), u2f(d.y), u2f(d.z)};
         return ls;
     }
+    CRT_HD LightSample sample(float rv0, float rv1, float rv2) const { return finish(fetch(rv0), rv1, rv2); }
 };
 CRT_HD float geometry_term(f3 p0, f3 n0, f3 p1, f3 n1)  // core.hpp:287-295
 {
@@ -236,39 +255,67 @@ CRT_HD Opt make_opt(const crt_options& o)
 
 // RIS over the emissive triangles: generate_candidate (10_restir_di.cu:78-111) and 09_ris.cu:66-100.
 // Randoms are drawn left to right: light pick, two barycentric randoms, then the reservoir's u.
+// One candidate: Reservoir::update (reservoir.hpp:22-29) with weight p_hat / light_pdf
+CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, float inv_n, float u, bool shadowed, Res& r)
+{
+    const float light_pdf = inv_n * 1.0f / ls.area;  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
+    const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
+    const float weight = p_hat / light_pdf;
+    r.w_sum += weight;
+    r.M += 1;
+    if (u < weight / r.w_sum)
+    {
+        r.s.hp = ls.p;
+        r.s.hn = ls.n;
+        r.s.rad = ls.emissive;
+        r.s.op = surf.p;
+        r.s.on = surf.n;
+        r.s.vis = 0;
+    }
+}
+// The four randoms of a candidate do not depend on earlier candidates, so the light records of kRisBatch
+// candidates are requested before the first one is used: kRisBatch gathers in flight per thread instead of one
+// (the loop was latency-bound on that gather: profiles/r1/source_g_k_generate_candidate.txt, 59 % long-scoreboard).
+#ifndef CRT_RIS_BATCH
+#define CRT_RIS_BATCH 4
+#endif
+constexpr int kRisBatch = CRT_RIS_BATCH;
 template <class L>
 CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int count, bool shadowed, Pcg& rng)
 {
     Res r = empty_res();
     const float inv_n = 1.0f / (float)lights.n;
-    for (int i = 0; i < count; ++i)
+    int i = 0;
+    for (; i + kRisBatch <= count; i += kRisBatch)
+    {
+        typename L::Raw raw[kRisBatch];
+        float r1[kRisBatch], r2[kRisBatch], u[kRisBatch];
+#pragma unroll
+        for (int b = 0; b < kRisBatch; ++b)
+        {
+            const float r0 = rng.next_f();
+            r1[b] = rng.next_f();
+            r2[b] = rng.next_f();
+            u[b] = rng.next_f();
+            raw[b] = lights.fetch(r0);
+        }
+#pragma unroll
+        for (int b = 0; b < kRisBatch; ++b) ris_update(bvh, surf, lights.finish(raw[b], r1[b], r2[b]), inv_n, u[b], shadowed, r);
+    }
+    for (; i < count; ++i)
     {
         const float r0 = rng.next_f();
         const float r1 = rng.next_f();
         const float r2 = rng.next_f();
-        const LightSample ls = lights.sample(r0, r1, r2);
-        const float light_pdf = inv_n * 1.0f / ls.area;  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
-        const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
-        const float weight = p_hat / light_pdf;
         const float u = rng.next_f();
-        r.w_sum += weight;  // Reservoir::update, reservoir.hpp:22-29
-        r.M += 1;
-        if (u < weight / r.w_sum)
-        {
-            r.s.hp = ls.p;
-            r.s.hn = ls.n;
-            r.s.rad = ls.emissive;
-            r.s.op = surf.p;
-            r.s.on = surf.n;
-            r.s.vis = 0;
-        }
+        ris_update(bvh, surf, lights.sample(r0, r1, r2), inv_n, u, shadowed, r);
     }
     return r;
 }
 
 // temporal_resampling body (10_restir_di.cu:172-233): `r` is this frame's reservoir, `prev` last frame's.
 template <class M>
-CRT_HD void temporal_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& opt, Res prev, Res& r, Pcg& rng)
+CRT_HD bool temporal_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& opt, Res prev, Res& r, Pcg& rng)
 {
     const int cap = 20 * opt.ris_count;  // M-cap, :186-188
     prev.M = prev.M < cap ? prev.M : cap;
@@ -279,8 +326,10 @@ CRT_HD void temporal_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& 
     const float u = rng.next_f();
     r.w_sum += weight;  // Reservoir::merge, reservoir.hpp:31-37
     r.M += prev.M;
-    if (u < weight / r.w_sum) r.s = prev.s;
+    const bool accepted = u < weight / r.w_sum;
+    if (accepted) r.s = prev.s;
     r.ucw = ucw_of(r, target_function(bvh, surf.p, surf.n, r.s.hp, r.s.hn, r.s.rad, opt.shadowed));
+    return accepted;  // false: the sample of `r` (this frame's candidate) survived
 }
 
 // one neighbour of spatial_resampling (10_restir_di.cu:340-370); compares against the *running* reservoir

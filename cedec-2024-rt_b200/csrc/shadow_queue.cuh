@@ -10,7 +10,7 @@
 // still busy, so the warps stay full.  The result is written where the per-pixel code would have put it
 // (the reservoir's visibility byte, or the shaded pixel), bit for bit.
 #pragma once
-#include "restir_pixel.cuh"
+#include "restir_fast.cuh"
 
 namespace crt
 {
@@ -62,15 +62,17 @@ __device__ __forceinline__ void queue_push(const ShadowQueue& q, bool has, const
 
 enum
 {
-    kEpiReservoirVisibility = 0,  // reservoirs[pix].sample.visibility = !occluded   (generate_candidate)
-    kEpiResolve = 1               // accumulation[pix] (+)= brdf*G*V*radiance*ucw     (resolve)
+    kEpiReservoirVisibility = 0,  // reservoirs[pix].sample.visibility = !occluded   (generate_candidate, AoS)
+    kEpiResolve = 1,              // accumulation[pix] (+)= brdf*G*V*radiance*ucw     (resolve)
+    kEpiSoaVisibility = 2         // fused frame: set the visibility bit of the SoA reservoir (restir_fast.cuh)
 };
 
 struct ShadowSink
 {
     crt_reservoir* reservoirs;  // kEpiReservoirVisibility
-    crt_float4* accumulation;   // kEpiResolve
+    crt_float4* accumulation;   // kEpiResolve*
     int accumulate;
+    uint32_t* soa_plane2;       // kEpiSoaVisibility: plane 2 of the SoA reservoir buffer (M | visibility << 31 in word 2)
 };
 
 // the shading factors stay in the queue record until the ray is decided (keeps the walk's register count down)
@@ -82,6 +84,11 @@ __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const Sh
     {
         // word 15 of the 19-word Reservoir holds `bool visibility` (+ 3 padding bytes)
         ((uint32_t*)(sink.reservoirs + pix))[15] = occluded ? 0u : 1u;
+    }
+    else if (EPI == kEpiSoaVisibility)
+    {
+        // the reservoir was stored with visibility = false; only this thread touches the word now
+        if (!occluded) sink.soa_plane2[(size_t)pix * 4 + 2] |= kVisBit;
     }
     else
     {

@@ -4,9 +4,11 @@
 //
 //   restir_di_headless --scene assets/blocks_restir.tri[.xz] [--tile NX NZ DX DZ] [--size W H] [--frames N]
 //                      [--eye x y z] [--lookat x y z] [--no-temporal] [--no-spatial] [--no-accumulate]
-//                      [--out image.ppm] [--dump-accum file.f32]
+//                      [--out image.ppm] [--dump-accum file.f32] [--fused]
 //
-// --scene takes the bytes of the reference loader's std::vector<Triangle> (oracle/stage_assets.py stages them;
+// --fused issues one crt_restir_di_frame call per frame instead of the launch list (same image, see cedecrt.h).
+//
+// --scene takes the raw bytes of a std::vector<Triangle> as the reference loader produces it (assets/*.tri;
 // .xz is piped through `xz -dc`) or, with a name ending in .obj, a Wavefront OBJ read by obj_scene.hpp.
 #include <cmath>
 #include <cstdio>
@@ -38,6 +40,7 @@ static std::vector<crt_triangle> load_tri_cache(const std::string& path)
 int main(int argc, char** argv)
 {
     std::string scene, out_ppm, dump_accum;
+    bool fused = false;
     int width = 1920, height = 1080, frames = 4, tile_nx = 1, tile_nz = 1;
     float tile_dx = 130.0f, tile_dz = 82.0f;
     float eye[3] = {-0.579885f, 22.194597f, -6.567105f}, center[3] = {5.224952f, 20.847435f, 1.431192f};  // :188-189
@@ -72,6 +75,7 @@ int main(int argc, char** argv)
         else if (a == "--no-temporal") options.use_temporal_resampling = 0;
         else if (a == "--no-spatial") options.use_spatial_resampling = 0;
         else if (a == "--no-accumulate") options.accumulate = 0;
+        else if (a == "--fused") fused = true;
         else if (a == "--out") { need(1); out_ppm = argv[++i]; }
         else if (a == "--dump-accum") { need(1); dump_accum = argv[++i]; }
         else
@@ -155,6 +159,16 @@ int main(int argc, char** argv)
             crt_raygen_lookat(&rayGen, eye, center, up, 3.14159265358979323846f / 4.0f, width, height);
             Stopwatch sw(device);
             sw.start();
+            if (fused)
+            {
+                auto view = [](auto& b) { return crt_buffer{b.data(), b.size() | (1ull << 63)}; };
+                const crt_restir_buffers bufs = {view(pixel_buffer), view(accumulation_buffer), view(visibility_buffer),
+                                                 view(reservoir_buffer0), view(reservoir_buffer1), view(temporal_reservoir_buffer)};
+                CRT_CHECKED(crt_restir_di_frame(device.ctx(), width, height, frame, geom, view(triangle_buffer), rayGen, cameraOrig,
+                                                view(light_buffer), options, &bufs));
+            }
+            else
+            {
             shader.launch("raycast",
                           ShaderArgument().value(width).value(height).value(geom).ptr(&triangle_buffer).ptr(&rayGen).ptr(&visibility_buffer),
                           grid, 1, 1, 256, 1, 1);
@@ -185,6 +199,7 @@ int main(int argc, char** argv)
                           grid, 1, 1, 256, 1, 1);
             shader.launch("tone_mapping", ShaderArgument().ptr(&pixel_buffer).ptr(&accumulation_buffer).value(width).value(height),
                           grid, 1, 1, 256, 1, 1);
+            }
             sw.stop();
             CRT_CHECKED(crt_memcpy_d2h_async(device.ctx(), host_pixels.data(), pixel_buffer.data(), pixel_buffer.bytes()));
             device.synchronize();

@@ -87,6 +87,13 @@ class _Buffer(C.Structure):
     _fields_ = [("data", C.c_void_p), ("size_and_flag", C.c_uint64)]
 
 
+class RestirBuffers(C.Structure):
+    """crt_restir_buffers: the frame's six TypedBuffers (10_restir_di.cpp:96-122) for the fused frame calls"""
+
+    _fields_ = [("pixels", _Buffer), ("accumulation", _Buffer), ("visibility", _Buffer), ("reservoir0", _Buffer),
+                ("reservoir1", _Buffer), ("temporal", _Buffer)]
+
+
 assert C.sizeof(Options) == 48 and C.sizeof(RayGenerator) == 36 and C.sizeof(_Buffer) == 16
 
 
@@ -115,6 +122,8 @@ def _load():
         "crt_sync": [P],
         "crt_timer_start": [P],
         "crt_timer_stop_ms": [P, C.POINTER(C.c_float)],
+        "crt_profile_begin": [P],
+        "crt_profile_end": [P, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), I, C.POINTER(I)],
         "crt_build_geometry": [P, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)],
         "crt_destroy_geometry": [P, G],
         "crt_geometry_stats": [G, C.POINTER(C.c_double)],
@@ -134,6 +143,15 @@ def _load():
         "crt_path_trace_08": [P, I, I, I, G, B, B, RayGenerator, Options, B],
         "crt_path_trace_09": [P, I, I, I, G, B, B, RayGenerator, Options, B],
         "crt_ao_06": [P, B, RayGenerator, I, I, G, B, I],
+        "crt_restir_di_frame": [P, I, I, I, G, B, RayGenerator, Float3, B, Options, C.POINTER(RestirBuffers)],
+        "crt_restir_frame_begin": [P, I, I, I, G, B, RayGenerator, Float3, B, Options, C.POINTER(RestirBuffers)],
+        "crt_restir_spatial_pass": [P, I, I, I, I, G, B, Float3, Options, C.POINTER(RestirBuffers)],
+        "crt_restir_frame_end": [P, I, I, G, B, Float3, Options, C.POINTER(RestirBuffers)],
+        "crt_restir_output_buffer": [Options, C.POINTER(RestirBuffers), C.POINTER(B)],
+        "crt_restir_is_fused": [Options],
+        "crt_restir_class_plane": [P, C.POINTER(C.c_void_p)],
+        "crt_reservoir_export_aos": [P, I, I, B, B],
+        "crt_reservoir_import_aos": [P, I, I, B, B],
         "crt_launch": [P, C.c_char_p, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                        C.c_uint],
     }
@@ -295,6 +313,15 @@ class Runtime:
         self._check(self.lib.crt_timer_stop_ms(self.ctx, C.byref(ms)))
         return ms.value
 
+    def profile_begin(self):
+        self._check(self.lib.crt_profile_begin(self.ctx))
+
+    def profile_end(self, cap=4096):
+        """[(kernel name, ms)] for every launch since profile_begin, in launch order"""
+        names, ms, n = C.create_string_buffer(cap * 40), (C.c_float * cap)(), C.c_int()
+        self._check(self.lib.crt_profile_end(self.ctx, names, len(names), ms, cap, C.byref(n)))
+        return list(zip(names.value.decode().split("\n")[:n.value], list(ms)[:n.value]))
+
     # -- buffers
     def buffer(self, dtype, n):
         return TypedBuffer(self, dtype, n)
@@ -379,6 +406,39 @@ class Runtime:
     def ao(self, pixels, raygen, W, H, geom, triangles, n_rays=64):
         self._check(self.lib.crt_ao_06(self.ctx, pixels.arg(), raygen, W, H, geom.handle, triangles.arg(), n_rays))
 
+    # -- fused frame (include/cedecrt.h: crt_restir_di_frame and its staged form)
+    @staticmethod
+    def restir_buffers(pixels, accumulation, visibility, reservoir0, reservoir1, temporal):
+        return RestirBuffers(pixels.arg(), accumulation.arg(), visibility.arg(), reservoir0.arg(), reservoir1.arg(),
+                             temporal.arg())
+
+    def restir_di_frame(self, W, H, frame, geom, triangles, raygen, eye, lights, options, bufs):
+        self._check(self.lib.crt_restir_di_frame(self.ctx, W, H, frame, geom.handle, triangles.arg(), raygen,
+                                                 Float3(*eye), lights.arg(), options, C.byref(bufs)))
+
+    def restir_frame_begin(self, W, H, frame, geom, triangles, raygen, eye, lights, options, bufs):
+        self._check(self.lib.crt_restir_frame_begin(self.ctx, W, H, frame, geom.handle, triangles.arg(), raygen,
+                                                    Float3(*eye), lights.arg(), options, C.byref(bufs)))
+
+    def restir_spatial_pass(self, W, H, frame, pas, geom, triangles, eye, options, bufs):
+        self._check(self.lib.crt_restir_spatial_pass(self.ctx, W, H, frame, pas, geom.handle, triangles.arg(),
+                                                     Float3(*eye), options, C.byref(bufs)))
+
+    def restir_frame_end(self, W, H, geom, triangles, eye, options, bufs):
+        self._check(self.lib.crt_restir_frame_end(self.ctx, W, H, geom.handle, triangles.arg(), Float3(*eye), options,
+                                                  C.byref(bufs)))
+
+    def restir_class_plane(self):
+        p = C.c_void_p()
+        self._check(self.lib.crt_restir_class_plane(self.ctx, C.byref(p)))
+        return p.value
+
+    def reservoir_export_aos(self, W, H, soa, aos_out):
+        self._check(self.lib.crt_reservoir_export_aos(self.ctx, W, H, soa.arg(), aos_out.arg()))
+
+    def reservoir_import_aos(self, W, H, aos_in, soa):
+        self._check(self.lib.crt_reservoir_import_aos(self.ctx, W, H, aos_in.arg(), soa.arg()))
+
     def launch(self, name, *args):
         """Shader::launch(name, ShaderArgument...) (shader.hpp:179-199): args are ctypes values / structures;
         TypedBuffer arguments are passed as their 16-byte device view, Geometry as its handle."""
@@ -405,8 +465,10 @@ class RestirDI:
     """The application loop of examples/10_restir_di/10_restir_di.cpp:96-122,184-226,229-380, headless:
     buffers live on the device, one `frame()` issues the reference's launch list on the context's stream."""
 
-    def __init__(self, rt, width, height, triangles_host, eye, lookat_pt, options=None):
-        self.rt, self.W, self.H = rt, width, height
+    def __init__(self, rt, width, height, triangles_host, eye, lookat_pt, options=None, fused=False):
+        """fused=False: the reference's launch list, one crt_* call per kernel, AoS reservoir buffers (drop-in mode);
+        fused=True: one crt_restir_di_frame call per frame (SoA reservoirs inside the same buffers)."""
+        self.rt, self.W, self.H, self.fused = rt, width, height, fused
         n = width * height
         self.options = options or Options()
         self.eye = tuple(float(np.float32(v)) for v in eye)
@@ -425,11 +487,31 @@ class RestirDI:
         self.frame_index = 0
         rt.clear(self.accumulation, width, height)
 
+    def output_reservoirs(self):
+        """final reservoirs of the last frame in the reference's AoS layout (host numpy array)"""
+        if not self.fused or not lib().crt_restir_is_fused(self.options):
+            return self.output.to_host()
+        bufs = self.rt.restir_buffers(self.pixels, self.accumulation, self.visibility, self.reservoir0,
+                                      self.reservoir1, self.temporal)
+        out = _Buffer()
+        lib().crt_restir_output_buffer(self.options, C.byref(bufs), C.byref(out))
+        src = next(b for b in (self.reservoir0, self.reservoir1, self.temporal) if b.ptr == out.data)
+        return self.export_aos(src)
+
+    def export_aos(self, buf):
+        tmp = self.rt.buffer(RESERVOIR, self.W * self.H)
+        self.rt.reservoir_export_aos(self.W, self.H, buf, tmp)
+        return tmp.to_host()
+
     def frame(self):
         rt, W, H, o, g, t, v, eye = (self.rt, self.W, self.H, self.options, self.geom, self.triangles,
                                      self.visibility, self.eye)
         self.frame_index += 1
         f = self.frame_index
+        if self.fused:
+            bufs = rt.restir_buffers(self.pixels, self.accumulation, v, self.reservoir0, self.reservoir1, self.temporal)
+            rt.restir_di_frame(W, H, f, g, t, self.raygen, eye, self.lights, o, bufs)
+            return
         rt.raycast(W, H, g, t, self.raygen, v)
         rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
         rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)

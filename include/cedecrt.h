@@ -106,6 +106,13 @@ int crt_sync(crt_ctx* ctx);                                                     
 int crt_timer_start(crt_ctx* ctx);
 int crt_timer_stop_ms(crt_ctx* ctx, float* ms);
 
+/* per-kernel device times (the breakdown behind the reference's single on-screen "kernel: x ms",
+ * 10_restir_di.cpp:382-383,410): between begin and end every kernel launched through this context is followed by
+ * an event; end synchronises and returns, per launch in order, a name ('\n'-separated) and the milliseconds
+ * since the previous launch finished */
+int crt_profile_begin(crt_ctx* ctx);
+int crt_profile_end(crt_ctx* ctx, char* names, size_t names_cap, float* ms, int ms_cap, int* count);
+
 /* RayGenerator::lookat (common/camera.hpp:11-25), evaluated on the host like the reference does */
 void crt_raygen_lookat(crt_raygen* rg, const float eye[3], const float center[3], const float up[3], float fovy,
                        int width, int height);
@@ -168,6 +175,48 @@ int crt_path_trace_09(crt_ctx* ctx, int width, int height, int frame, crt_geomet
 /* examples/06_ao_hiprt/06_ao_hiprt.cu:35-37; n_rays replaces the hard-coded N_Rays = 64 (:71) */
 int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int width, int height, crt_geometry geom,
               crt_buffer triangles, int n_rays);
+
+/* ---- fused frame ("fast mode").  One call replaces the launch list of a frame
+ * (examples/10_restir_di/10_restir_di.cpp:270-372: raycast ... tone_mapping) with identical results in
+ * `accumulation`, `pixels` and `visibility`.  The three TypedBuffer<Reservoir> allocations (W*H*76 bytes each, as
+ * the reference allocates them, :112-122) are used as OPAQUE storage: inside, reservoirs are planar SoA
+ *   plane p (p = 0..3) at byte offset p*16*W*H, 16 bytes per pixel; plane 4 at 64*W*H, 8 bytes per pixel
+ *   (field order: csrc/restir_fast.cuh), pixel order = the reference's pixel_idx (bottom-up rows),
+ * candidate generation and temporal resampling are one kernel that rewrites `temporal` in place (no
+ * save_temporal_reservoir), spatial pass 0 reads `temporal` and writes reservoir1, later passes ping-pong
+ * reservoir1 <-> reservoir0, and tone mapping is part of resolve.  crt_reservoir_export_aos converts a buffer to
+ * the reference's AoS for inspection.  With use_shadowed_target_function the same calls run the per-kernel path on
+ * AoS buffers instead (crt_restir_is_fused tells which); do not mix the two on one set of buffers. */
+typedef struct
+{
+    crt_buffer pixels;        /* TypedBuffer<uint8_t>   4*W*H   (10_restir_di.cpp:96-97)  */
+    crt_buffer accumulation;  /* TypedBuffer<float4>    W*H     (:102-103) */
+    crt_buffer visibility;    /* TypedBuffer<Visibility> W*H    (:108-109) */
+    crt_buffer reservoir0;    /* TypedBuffer<Reservoir> W*H     (:113-114) */
+    crt_buffer reservoir1;    /*                                (:117-118) */
+    crt_buffer temporal;      /* zero it once before frame 1    (:121-122) */
+} crt_restir_buffers;
+int crt_restir_di_frame(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                        crt_raygen raygen, crt_float3 eye, crt_buffer lights, crt_options options,
+                        const crt_restir_buffers* buffers);
+/* the same frame in three stages, for hosts that exchange halo rows between them (multi-GPU row slabs):
+ * begin = raycast + candidates + temporal; one call per spatial pass; end = resolve + tone mapping */
+int crt_restir_frame_begin(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                           crt_raygen raygen, crt_float3 eye, crt_buffer lights, crt_options options,
+                           const crt_restir_buffers* buffers);
+int crt_restir_spatial_pass(crt_ctx* ctx, int width, int height, int frame, int pass, crt_geometry geom,
+                            crt_buffer triangles, crt_float3 eye, crt_options options,
+                            const crt_restir_buffers* buffers);
+int crt_restir_frame_end(crt_ctx* ctx, int width, int height, crt_geometry geom, crt_buffer triangles, crt_float3 eye,
+                         crt_options options, const crt_restir_buffers* buffers);
+/* which of the three buffers holds the reservoirs resolve reads (the reference's buf_output, :324-336) */
+int crt_restir_output_buffer(crt_options options, const crt_restir_buffers* buffers, crt_buffer* out);
+int crt_restir_is_fused(crt_options options);
+/* device pointer to the W*H-byte pixel-class plane of the last fused frame (1 = diffuse surface, 0 = sky or
+ * emissive): the only per-frame data besides reservoir rows a multi-GPU host has to exchange */
+int crt_restir_class_plane(crt_ctx* ctx, void** out);
+int crt_reservoir_export_aos(crt_ctx* ctx, int width, int height, crt_buffer soa_storage, crt_buffer aos_out);
+int crt_reservoir_import_aos(crt_ctx* ctx, int width, int height, crt_buffer aos_in, crt_buffer soa_storage);
 
 /* Shader::launch call shape (common/shader.hpp:179-199): kernel by name, params as the void*[] that
  * ShaderArgument builds (pointers to by-value arguments, in order), grid/block accepted and ignored.

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "bvh_build.cuh"
-#include "restir_pixel.cuh"
+#include "restir_fast.cuh"
 
 using namespace crt;
 
@@ -326,5 +326,69 @@ extern "C"
                                                : px_ao<Math<0>>(p, *rg, W, H, bvh, (const float*)tris, n_rays);
                });
         return 0;
+    }
+
+    // ---- the fused frame (csrc/kernels_fast.cu: crt_restir_di_frame), same kernel sequence, rays traced inline.
+    // temporal / res_a / res_b: planar SoA storage of W*H*76 bytes each (restir_fast.cuh: SoaStore).
+    // Final spatial output: res_a for an odd number of passes, res_b for an even one, `temporal` if spatial is off.
+    void emu_restir_frame_fast(int W, int H, int frame, void* gp, const crt_triangle* tris, const crt_raygen* rg,
+                               const float* eye_p, const uint32_t* lights, int nlights, const crt_options* options,
+                               crt_visibility* vis, char* temporal, char* res_a, char* res_b, crt_float4* accum,
+                               uint32_t* pixels)
+    {
+        const Bvh bvh = ((EmuGeom*)gp)->view();
+        const float* t60 = (const float*)tris;
+        const f3 eye = v3(eye_p);
+        const Opt opt = make_opt(*options);
+        const size_t n = (size_t)W * H;
+        std::vector<char> g0(n * 16), g1(n * 8);
+        std::vector<uint8_t> cls(n, 0);
+        const GBuf g{g0.data(), g1.data(), cls.data()};
+        const SoaStore T{temporal, n}, A{res_a, n}, B{res_b, n};
+        const LightsIndexed L{t60, lights, (uint32_t)nlights};
+        launch(W, H, [&](Pix p) { px_raycast(p, W, H, bvh, *rg, vis); });
+        launch(W, H, [&](Pix p)
+               {
+                   const DeferredRay d = g_math_mode ? px_candidate_temporal<Math<1>>(p, frame, bvh, t60, vis, eye, L, opt, T, g)
+                                                     : px_candidate_temporal<Math<0>>(p, frame, bvh, t60, vis, eye, L, opt, T, g);
+                   if (d.want)
+                   {
+                       Hit h;
+                       if (!trace<true>(bvh, d.org, d.dir, 0.0f, 0.99f, h)) *T.mvis_word(p.idx) |= kVisBit;
+                   }
+               });
+        SoaStore in = T, out = A;
+        if (opt.spatial)
+            for (int pass = 0; pass < options->spatial_resampling_passes; pass++)
+            {
+                if (pass == 1) { in = A; out = B; }
+                else if (pass > 1) std::swap(in, out);
+                launch(W, H, [&](Pix p)
+                       {
+                           g_math_mode ? px_spatial_fast<Math<1>>(p, W, H, frame, pass, bvh, eye, opt, in, out, g)
+                                       : px_spatial_fast<Math<0>>(p, W, H, frame, pass, bvh, eye, opt, in, out, g);
+                       });
+            }
+        const SoaStore fin = opt.spatial && options->spatial_resampling_passes > 0 ? out : T;
+        launch(W, H, [&](Pix p)
+               {
+                   DeferredShade sh{{0, 0, 0}, {0, 0, 0}, 0.0f};
+                   const DeferredRay d = px_resolve_fast(p, accum, t60, vis, fin, g, sh);
+                   if (!d.want) return;
+                   Hit h;
+                   const float V = trace<true>(bvh, d.org, d.dir, 0.0f, 0.99f, h) ? 0.0f : 1.0f;
+                   write_accum(accum, p.idx, sh.bg * V * sh.rad * sh.ucw, opt.accumulate);  // shadow_epilogue<kEpiResolve>
+               });
+        orc_tone_mapping(pixels, accum, W, H);
+    }
+    void emu_soa_to_aos(const char* soa, crt_reservoir* aos, long n)
+    {
+        const SoaStore s{const_cast<char*>(soa), (size_t)n};
+        for (long i = 0; i < n; i++) soa_to_aos(s, aos, (int)i);
+    }
+    void emu_aos_to_soa(const crt_reservoir* aos, char* soa, long n)
+    {
+        const SoaStore s{soa, (size_t)n};
+        for (long i = 0; i < n; i++) aos_to_soa(aos, s, (int)i);
     }
 }

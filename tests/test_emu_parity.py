@@ -160,3 +160,111 @@ def test_degenerate_inputs(emu, port):
             outs.append(o.raycast(W, H, g, tris, o.lookat(*CAM_CB, W, H)))
             o.geom_free(g)
         assert same(outs[0]["index"], outs[1]["index"]) and same(outs[0]["uv"], outs[1]["uv"])
+
+
+# ---------------------------------------------------------------------------------------------- fused frame
+class EmuFusedFrame:
+    """Drives emu_restir_frame_fast (the kernel sequence of crt_restir_di_frame, csrc/kernels_fast.cu) on planar
+    SoA reservoir storage and converts back to the reference's AoS for comparison."""
+
+    def __init__(self, emu, W, H, tris, g, eye, center, opt):
+        self.L, self.W, self.H, self.tris, self.g, self.opt = emu.lib, W, H, tris, g, opt
+        self.eye = np.asarray(eye, np.float32)
+        self.rg = emu.lookat(eye, center, W, H)
+        self.lights = orc.light_indices(tris)
+        n = W * H
+        self.vis = np.zeros(n, orc.VISIBILITY)
+        self.T, self.A, self.B = (np.zeros(n * 76, np.uint8) for _ in range(3))
+        self.accum = np.zeros((n, 4), np.float32)
+        self.pixels = np.zeros(n, np.uint32)
+        self.frame = 0
+
+    def step(self):
+        self.frame += 1
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        lights = self.lights if len(self.lights) else np.zeros(1, np.uint32)
+        self.L.emu_restir_frame_fast(self.W, self.H, self.frame, self.g, p(self.tris), p(self.rg), p(self.eye),
+                                     p(lights), len(self.lights), p(self.opt), p(self.vis), p(self.T), p(self.A),
+                                     p(self.B), p(self.accum), p(self.pixels))
+
+    def aos(self, soa):
+        out = np.zeros(self.W * self.H, orc.RESERVOIR)
+        self.L.emu_soa_to_aos(soa.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_long(len(out)))
+        return out
+
+    def output(self):
+        passes = int(self.opt["spatial_resampling_passes"])
+        if not self.opt["use_spatial_resampling"] or passes == 0:
+            return self.aos(self.T)
+        return self.aos(self.A if passes % 2 else self.B)
+
+
+def diffuse_mask(vis, tris):
+    em = (tris["emissive"] > 0).any(1)
+    m = vis["index"] >= 0
+    m[m] = ~em[vis["index"][m]]
+    return m
+
+
+FUSED_VARIANTS = [
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, spatial_resampling_passes=2),
+    dict(accumulate=0, use_temporal_resampling=1, use_spatial_resampling=1, spatial_resampling_passes=1),
+    dict(accumulate=1, use_temporal_resampling=0, use_spatial_resampling=1),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=0),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, use_visibility_reuse=0),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, ris_sample_count=7,
+         spatial_resampling_sample_count=3, spatial_resampling_radius=10.0),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("variant", range(len(FUSED_VARIANTS)))
+def test_fused_frame_equals_kernel_chain(emu, port, variant, mode):
+    """the fused data flow (SoA planes, candidate+temporal in one body, in-place temporal buffer, conditional
+    visibility-reuse ray, G-buffer, tone mapping in the resolve epilogue) gives the oracle's buffers bit for bit"""
+    tris = lit_blocks_ao()
+    W, H = 96, 54
+    opt = orc.make_options(**FUSED_VARIANTS[variant])
+    port.set_math_mode(mode)
+    emu.set_math_mode(mode)
+    try:
+        g = port.geom_build(tris)
+        ch = orc.RestirChain(port, W, H, tris, g, *CAM_AO, opt)
+        ge = emu.geom_build(tris)
+        fu = EmuFusedFrame(emu, W, H, tris, ge, *CAM_AO, opt)
+        for _ in range(3):
+            ch.step()
+            fu.step()
+            if not opt["use_spatial_resampling"]:
+                # the reference still copies buf0 -> buf1 in its (disabled) spatial passes; same reservoirs
+                pass
+        d = diffuse_mask(ch.vis, tris)
+        assert d.sum() > 1000
+        assert same(ch.vis["index"], fu.vis["index"]) and same(ch.vis["uv"], fu.vis["uv"])
+        assert reservoir_mismatch(ch.temporal, fu.aos(fu.T)) == 0
+        assert reservoir_mismatch(ch.out[d], fu.output()[d]) == 0
+        assert same(ch.accum, fu.accum)
+        assert same(port.tone_mapping(ch.accum, W, H), fu.pixels.view(np.uint8))
+        port.geom_free(g)
+        emu.geom_free(ge)
+    finally:
+        port.set_math_mode(0)
+        emu.set_math_mode(0)
+
+
+def test_soa_aos_round_trip(emu):
+    rng = np.random.default_rng(5)
+    n = 1000
+    a = np.zeros(n, orc.RESERVOIR)
+    for f in ("origin_position", "origin_normal", "hit_position", "hit_normal", "radiance"):
+        a[f] = rng.standard_normal((n, 3)).astype(np.float32)
+    a["visibility"] = rng.integers(0, 2, n)
+    a["w_sum"], a["ucw"] = rng.random(n, np.float32), rng.random(n, np.float32)
+    a["M"] = rng.integers(0, 2**31 - 1, n)
+    soa = np.zeros(n * 76, np.uint8)
+    emu.lib.emu_aos_to_soa(a.ctypes.data_as(C.c_void_p), soa.ctypes.data_as(C.c_void_p), C.c_long(n))
+    b = np.zeros(n, orc.RESERVOIR)
+    emu.lib.emu_soa_to_aos(soa.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_long(n))
+    assert reservoir_mismatch(a, b) == 0
+    assert not soa[72 * n:].any()  # 72 of the 76 bytes per pixel are used

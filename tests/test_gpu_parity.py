@@ -14,6 +14,7 @@ import os
 import numpy as np
 import pytest
 
+import cedecrt
 import orc
 from helpers import DeviceAsOracle, reservoir_mismatch, same, small_scene
 
@@ -333,3 +334,101 @@ def test_full_frame_properties_4k_tiled(rt):
     app2.frame()
     assert same(app2.accumulation.to_host(), app.accumulation.to_host())
     assert same(app2.visibility.to_host()["index"], idx)
+
+
+# ---------------------------------------------------------------------------------------------- fused frame
+FUSED_VARIANTS = [
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, spatial_resampling_passes=2),
+    dict(accumulate=0, use_temporal_resampling=1, use_spatial_resampling=1, spatial_resampling_passes=1),
+    dict(accumulate=1, use_temporal_resampling=0, use_spatial_resampling=1),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=0),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, use_visibility_reuse=0),
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, use_shadowed_target_function=1),  # per-kernel fallback
+    dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1, ris_sample_count=7,
+         spatial_resampling_sample_count=3, spatial_resampling_radius=10.0),
+]
+
+
+def diffuse_mask(vis, tris):
+    em = (tris["emissive"] > 0).any(1)
+    m = vis["index"] >= 0
+    m[m] = ~em[vis["index"][m]]
+    return m
+
+
+@pytest.mark.parametrize("variant", range(len(FUSED_VARIANTS)))
+def test_fused_frame_bit_exact_vs_oracle(rt, port, variant):
+    """crt_restir_di_frame (SoA reservoirs, fused candidate+temporal, conditional visibility-reuse ray, G-buffer,
+    tone mapping in the resolve epilogue) against the oracle's kernel-by-kernel chain, exact math mode: every
+    buffer the reference's loop leaves behind is reproduced bit for bit."""
+    tris = lit_blocks_ao()
+    W, H = 160, 90
+    kw = FUSED_VARIANTS[variant]
+    opt = orc.make_options(**kw)
+    rt.set_math_mode(cedecrt.MATH_EXACT)
+    port.set_math_mode(1)
+    try:
+        g = port.geom_build(tris)
+        ch = orc.RestirChain(port, W, H, tris, g, *CAM_AO, opt)
+        app = cedecrt.RestirDI(rt, W, H, tris, *CAM_AO, cedecrt.Options(**kw), fused=True)
+        for _ in range(3):
+            ch.step()
+            app.frame()
+        vis = app.visibility.to_host()
+        assert same(vis["index"], ch.vis["index"]) and same(vis["uv"], ch.vis["uv"])
+        d = diffuse_mask(ch.vis, tris)
+        assert d.sum() > 3000
+        if cedecrt.lib().crt_restir_is_fused(app.options):
+            temporal = app.export_aos(app.temporal)
+        else:
+            temporal = app.temporal.to_host()
+        assert reservoir_mismatch(ch.temporal, temporal) == 0
+        assert reservoir_mismatch(ch.out[d], app.output_reservoirs()[d]) == 0
+        acc = app.accumulation.to_host().view(np.float32).reshape(-1, 4)
+        assert same(acc, ch.accum)
+        assert same(app.pixels.to_host(), port.tone_mapping(ch.accum, W, H))
+        port.geom_free(g)
+    finally:
+        rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+        port.set_math_mode(0)
+
+
+@pytest.mark.parametrize("scene", ["blocks_ao_lit", "blocks_restir"])
+def test_fused_equals_per_kernel_path_default_math(rt, scene):
+    """default (libdevice) math: the fused frame and the reference's launch list give identical images"""
+    if scene == "blocks_restir":
+        tris = staged("blocks_restir")
+        W, H, cam, frames = 960, 540, CAM_RESTIR, 3
+    else:
+        tris, W, H, cam, frames = lit_blocks_ao(), 320, 180, CAM_AO, 4
+    kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    a = cedecrt.RestirDI(rt, W, H, tris, *cam, cedecrt.Options(**kw), fused=False)
+    b = cedecrt.RestirDI(rt, W, H, tris, *cam, cedecrt.Options(**kw), fused=True)
+    for _ in range(frames):
+        a.frame()
+        b.frame()
+    assert same(a.visibility.to_host(), b.visibility.to_host())
+    assert same(a.accumulation.to_host(), b.accumulation.to_host())
+    assert same(a.pixels.to_host(), b.pixels.to_host())
+    va = a.visibility.to_host()
+    d = diffuse_mask(va, tris)
+    assert reservoir_mismatch(a.temporal.to_host(), b.export_aos(b.temporal)) == 0
+    assert reservoir_mismatch(a.output.to_host()[d], b.output_reservoirs()[d]) == 0
+    assert float(a.accumulation.to_host().view(np.float32).reshape(-1, 4)[:, :3].sum()) > 0
+
+
+def test_reservoir_layout_round_trip(rt):
+    n_w, n_h = 64, 16
+    n = n_w * n_h
+    rng = np.random.default_rng(11)
+    a = np.zeros(n, cedecrt.RESERVOIR)
+    for f in ("origin_position", "origin_normal", "hit_position", "hit_normal", "radiance"):
+        a[f] = rng.standard_normal((n, 3)).astype(np.float32)
+    a["visibility"] = rng.integers(0, 2, n)
+    a["w_sum"], a["ucw"] = rng.random(n, np.float32), rng.random(n, np.float32)
+    a["M"] = rng.integers(0, 2**31 - 1, n)
+    d_a, d_s, d_b = rt.to_device(a), rt.buffer(cedecrt.RESERVOIR, n), rt.buffer(cedecrt.RESERVOIR, n)
+    rt.reservoir_import_aos(n_w, n_h, d_a, d_s)
+    rt.reservoir_export_aos(n_w, n_h, d_s, d_b)
+    assert reservoir_mismatch(a, d_b.to_host()) == 0
