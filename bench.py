@@ -6,7 +6,8 @@
 
 A "step" is one frame of the reference's frame loop (examples/10_restir_di/10_restir_di.cpp:229-380: raycast,
 generate_candidate, temporal_resampling, save_temporal_reservoir, 3 x spatial_resampling, resolve,
-tone_mapping) over BASELINE config 5: blocks_restir.obj tiled x6 (9 590 208 triangles, 875 892 lights),
+tone_mapping) — issued as the fused frame calls of include/cedecrt.h (--mode fused, default; identical images)
+or as the reference's launch list (--mode dropin) — over BASELINE config 5: blocks_restir.obj tiled x6 (9 590 208 triangles, 875 892 lights),
 3840x2160, temporal + spatial (5 neighbours, r = 30, 3 passes) + visibility reuse, accumulate.
 
 value  = W*H*K / device time of the K frames (CUDA events, max over ranks), buffers resident in HBM —
@@ -15,8 +16,9 @@ e2e    = the same loop including, every frame, the device->host copy of the RGBA
          memory (10_restir_di.cpp:386-389); the per-frame host inputs (RayGenerator, eye, Options) travel as
          kernel parameters.
 N > 1  : the frame is split into horizontal row slabs, one rank per GPU (strong scaling); scene and BVH are
-         replicated, the reservoir/visibility halo rows the spatial passes read are exchanged with NCCL
-         send/recv between slab neighbours.
+         replicated; the 87 halo rows of reservoirs the spatial passes read are stored by the producing rank
+         directly into its neighbours' buffers over NVLink (--halo p2p, csrc/slab_p2p.cu) or exchanged with
+         NCCL send/recv (--halo nccl, and always in --mode dropin).
 """
 import argparse
 import json
@@ -121,103 +123,7 @@ HBM_BOUND = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampli
              "candidate_temporal", "resolve_fast")
 
 
-class CudaArrayView:
-    """device memory owned by libcedecrt as a torch tensor (zero-copy, __cuda_array_interface__)"""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-class SlabRenderer:
-    """The frame loop over one GPU's row slab.  Buffers are full-size (pixel indices stay global) and are torch
-    tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
-
-    def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True):
-        import numpy as np
-
-        import cedecrt
-        import slabs
-
-        self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
-        self.c, self.slabs, self.fused = cedecrt, slabs, fused
-        self.rt = cedecrt.Runtime(torch.cuda.current_device())
-        assert torch.cuda.current_stream().cuda_stream != 0, "bench needs a non-default torch stream"
-        self.rt.set_stream(torch.cuda.current_stream().cuda_stream)
-        self.edges = [slabs.slab_rows(H, world, r)[0] for r in range(world)] + [H]
-        self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
-        self.plan = slabs.halo_plan(H, self.edges, rank) if world > 1 else []
-        self.rt.set_row_range(self.y0, self.y1)
-        self.options = cedecrt.Options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
-        self.eye = tuple(float(np.float32(v)) for v in cam[0])
-        self.raygen = cedecrt.lookat(cam[0], cam[1], W, H)
-        n = W * H
-        dev = torch.device("cuda", torch.cuda.current_device())
-
-        def tbuf(nbytes, dtype, count, zero=False):
-            t = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
-            return t, self.rt.wrap(t.data_ptr(), dtype, count)
-
-        self.t_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).to(dev)
-        self.triangles = self.rt.wrap(self.t_tris.data_ptr(), cedecrt.TRIANGLE, len(tris))
-        lights = cedecrt.light_indices(tris)
-        self.t_lights = torch.from_numpy(lights.view(np.uint8)).to(dev)
-        self.lights = self.rt.wrap(self.t_lights.data_ptr(), np.uint32, len(lights))
-        self.n_tris, self.n_lights = len(tris), len(lights)
-        self.geom = self.rt.build_geometry(self.triangles)
-        self.t_pix, self.pixels = tbuf(4 * n, np.uint8, 4 * n)
-        self.t_acc, self.accumulation = tbuf(16 * n, cedecrt.FLOAT4, n, zero=True)
-        self.t_vis, self.visibility = tbuf(16 * n, cedecrt.VISIBILITY, n, zero=True)
-        self.t_r0, self.reservoir0 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
-        self.t_r1, self.reservoir1 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
-        self.t_tmp, self.temporal = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True)
-        self.bufs = self.rt.restir_buffers(self.pixels, self.accumulation, self.visibility, self.reservoir0,
-                                           self.reservoir1, self.temporal)
-        self.host_pixels = torch.empty(4 * W * (self.y1 - self.y0), dtype=torch.uint8).pin_memory()
-        self.frame_index = 0
-        self.t_cls = None
-        self.halo_bytes = 0
-
-    def _rows(self, t, elem, a, b):
-        return t[(self.H - b) * self.W * elem:(self.H - a) * self.W * elem]
-
-    def exchange(self, t, layout):
-        if self.world > 1:
-            self.halo_bytes += self.slabs.exchange(self.dist, t, self.W, self.H, layout, self.plan)
-
-    def frame(self):
-        rt, W, H, o, g, t, v, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.visibility, self.eye
-        S = self.slabs
-        self.frame_index += 1
-        f = self.frame_index
-        if self.fused:
-            rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
-            if self.world > 1:
-                if self.t_cls is None:
-                    self.t_cls = self.torch.as_tensor(CudaArrayView(rt.restir_class_plane(), W * H), device="cuda")
-                self.exchange(self.t_cls, S.CLASS_PLANE)
-            for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
-                self.exchange(self.t_tmp if k == 0 else (self.t_r1 if k % 2 else self.t_r0), S.SOA_RESERVOIR)
-                rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
-            rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
-            return
-        rt.raycast(W, H, g, t, self.raygen, v)
-        self.exchange(self.t_vis, S.AOS_VISIBILITY)
-        rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
-        rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
-        rt.save_temporal_reservoir(W, H, self.reservoir0, self.temporal)
-        bi, bo, ti = self.reservoir0, self.reservoir1, self.t_r0
-        for k in range(o.spatial_resampling_passes):
-            if k != 0:
-                bi, bo = bo, bi
-                ti = self.t_r1 if ti is self.t_r0 else self.t_r0
-            self.exchange(ti, S.AOS_RESERVOIR)
-            rt.spatial_resampling(W, H, f, k, g, t, v, eye, o, bi, bo)
-        rt.resolve(self.accumulation, W, H, g, t, v, eye, o, bo)
-        rt.tone_mapping(self.pixels, self.accumulation, W, H)
-
-    def download_pixels(self):
-        src = self._rows(self.t_pix, 4, self.y0, self.y1)
-        self.host_pixels.copy_(src, non_blocking=True)
+from slabs import HALO as HALO_ROWS, SlabRenderer  # noqa: E402  (cedec-2024-rt_b200/python/slabs.py)
 
 
 def pixel_classes(torch, r):
@@ -252,8 +158,10 @@ def run_cuda(args):
     tris, cam, workload = load_workload()
     W, H = args.width, args.height
     fused = args.mode == "fused"
-    r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused)
+    r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
     stats = r.geom.stats()
+    if world > 1 and not args.no_balance:
+        r.calibrate()  # static camera: balance the slab heights on throw-away frames before the sequence starts
 
     def barrier():
         if world > 1:
@@ -344,8 +252,11 @@ def run_cuda(args):
                        "camera": "10_restir_di.cpp:188-189",
                        "mode": "fused frame (crt_restir_frame_begin / spatial_pass / frame_end, SoA reservoirs)" if fused
                                else "per-kernel launch list (drop-in, AoS reservoirs)",
-                       "partition": "%d row slab(s), halo %d rows, %d halo bytes sent per frame by rank 0" % (
-                           world, r.slabs.HALO, halo_bytes_per_frame),
+                       "slab_edges": r.edges,
+                       "partition": "%d row slab(s), halo %d rows, %s" % (
+                           world, HALO_ROWS, "halo rows stored directly into the neighbours' buffers over NVLink "
+                           "(cudaIpc peer pointers, csrc/slab_p2p.cu)" if r.p2p else
+                           "%d halo bytes sent per frame by rank 0 (NCCL send/recv)" % halo_bytes_per_frame),
                        "l2": "per-frame working set (3 x 600 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
                        "math": "libdevice float (reference NVRTC semantics), -fmad=false"},
             "grays_per_s": round(rays * args.steps / ms / 1e6, 4), "rays_per_frame": int(rays),
@@ -493,6 +404,9 @@ def main():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--cpu-rows", type=int, default=64, help="band height of the CPU arm's per-step sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal-height slabs (no calibration frames)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1, fused mode: halo rows by direct peer stores (default) or NCCL send/recv")
     ap.add_argument("--mode", default="fused", choices=["fused", "dropin"],
                     help="fused: one crt_restir_* frame call sequence (default); dropin: the reference's launch list")
     args = ap.parse_args()

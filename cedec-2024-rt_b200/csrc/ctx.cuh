@@ -28,6 +28,10 @@ struct crt_ctx
     // fused frame (kernels_fast.cu): G-buffer + pixel-class plane, 25 bytes per pixel, grown on demand
     void* gbuf = nullptr;
     size_t gbuf_pixels = 0;
+    // slab_p2p.cu: peer pointers of the neighbouring slabs and the exchange counter
+    crt_slab_links links = {};
+    bool links_set = false;
+    unsigned long long link_epoch = 0;
     int row_begin = 0, row_end = -1;  // rows of yi this context computes (crt_set_row_range); -1 = image height
     unsigned long long launches = 0;  // kernels launched through this context (bench.py: gpu_launches)
     // crt_profile_begin/end: an event after every launch; consecutive differences are per-kernel device times

@@ -22,8 +22,11 @@
 
 namespace crt
 {
+#ifndef CRT_CT_MINBLOCKS
+#define CRT_CT_MINBLOCKS 3  // 80 registers; measured best with kRisBatch = 2 (profiles/r1/tuning_j.txt)
+#endif
 template <class L, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
     k_candidate_temporal(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
                          L lights, crt_options options, SoaStore temporal, GBuf g, ShadowQueue q)
 {

@@ -277,7 +277,7 @@ CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, 
 // candidates are requested before the first one is used: kRisBatch gathers in flight per thread instead of one
 // (the loop was latency-bound on that gather: profiles/r1/source_g_k_generate_candidate.txt, 59 % long-scoreboard).
 #ifndef CRT_RIS_BATCH
-#define CRT_RIS_BATCH 4
+#define CRT_RIS_BATCH 2
 #endif
 constexpr int kRisBatch = CRT_RIS_BATCH;
 template <class L>

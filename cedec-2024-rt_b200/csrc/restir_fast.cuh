@@ -60,6 +60,7 @@ CRT_HD void store_u2(void* p, u2 v)
 //   plane 4 @ 64 n   float2  origin_normal.y, origin_normal.z
 // resolve reads planes 0-2 only; a neighbour merge reads everything but uses no w_sum.
 constexpr int kSoaPlanes = 5;
+constexpr int kHaloRows = 87;  // rows a spatial pass can reach beyond a slab: |offset| <= 86.4 px (10_restir_di.cu:309-313)
 CRT_HD size_t soa_plane_offset(int plane, size_t n) { return (size_t)plane * 16u * n; }
 CRT_HD size_t soa_plane_elem(int plane) { return plane < 4 ? 16u : 8u; }
 constexpr uint32_t kVisBit = 0x80000000u;

@@ -36,7 +36,10 @@ struct ShadowQueue
     uint32_t capacity;
 };
 
-constexpr int kRefillThreshold = 24;  // refetch when fewer lanes than this are still walking
+#ifndef CRT_REFILL
+#define CRT_REFILL 24
+#endif
+constexpr int kRefillThreshold = CRT_REFILL;  // refetch when fewer lanes than this are still walking
 
 #if defined(__CUDACC__)
 // warp-aggregated append; every lane of the warp must call it (has = whether this lane emits a ray)
@@ -144,8 +147,11 @@ constexpr int kPairCap = 128;      // (ray, triangle) pairs a warp tests per coo
 //                   (profiles/r1/source_c_trace_shadow_queue.txt).
 // A lane whose ray is decided takes the next ray from the global counter as soon as fewer than
 // kRefillThreshold lanes of its warp are still walking.
+#ifndef CRT_SHADOW_MINBLOCKS
+#define CRT_SHADOW_MINBLOCKS 8  // 64 registers, 32 warps/SM: measured 5 % faster than 6 (profiles/r1/tuning_j.txt)
+#endif
 template <int EPI>
-__global__ void __launch_bounds__(kShadowWarps * 32, 6) k_trace_shadow_queue(Bvh bvh, ShadowQueue q, ShadowSink sink)
+__global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_trace_shadow_queue(Bvh bvh, ShadowQueue q, ShadowSink sink)
 {
     __shared__ uint32_t s_pairs[kShadowWarps][kPairCap];
     __shared__ uint32_t s_occluded[kShadowWarps];

@@ -12,7 +12,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "..", "libcedecrt.so")
+# CRT_LIB_VARIANT=<tag>: load libcedecrt_<tag>.so (a tuning build, csrc/Makefile VARIANT=<tag>) instead
+_VARIANT = os.environ.get("CRT_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "..", "libcedecrt%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 # ---- reference struct layouts as numpy dtypes (host-side views of device buffers)
 _f3 = (np.float32, (3,))
@@ -94,6 +96,13 @@ class RestirBuffers(C.Structure):
                 ("reservoir1", _Buffer), ("temporal", _Buffer)]
 
 
+class SlabLinks(C.Structure):
+    """crt_slab_links (include/cedecrt.h): peer pointers of the neighbouring row slabs"""
+
+    _fields_ = [("up", C.c_void_p * 4), ("down", C.c_void_p * 4), ("up_flag", C.c_void_p), ("down_flag", C.c_void_p),
+                ("my_flags", C.c_void_p)]
+
+
 assert C.sizeof(Options) == 48 and C.sizeof(RayGenerator) == 36 and C.sizeof(_Buffer) == 16
 
 
@@ -152,6 +161,12 @@ def _load():
         "crt_restir_class_plane": [P, C.POINTER(C.c_void_p)],
         "crt_reservoir_export_aos": [P, I, I, B, B],
         "crt_reservoir_import_aos": [P, I, I, B, B],
+        "crt_ipc_export": [P, C.c_void_p, C.c_char_p],
+        "crt_ipc_open": [P, C.c_char_p, C.POINTER(C.c_void_p)],
+        "crt_ipc_close": [P, C.c_void_p],
+        "crt_restir_reserve": [P, I, I, C.POINTER(C.c_void_p)],
+        "crt_slab_set_links": [P, C.POINTER(SlabLinks)],
+        "crt_slab_exchange": [P, I, I, I, I, C.POINTER(RestirBuffers)],
         "crt_launch": [P, C.c_char_p, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                        C.c_uint],
     }
@@ -438,6 +453,28 @@ class Runtime:
 
     def reservoir_import_aos(self, W, H, aos_in, soa):
         self._check(self.lib.crt_reservoir_import_aos(self.ctx, W, H, aos_in.arg(), soa.arg()))
+
+    # -- multi-GPU row slabs with direct peer stores (csrc/slab_p2p.cu)
+    def ipc_export(self, ptr):
+        h = C.create_string_buffer(64)
+        self._check(self.lib.crt_ipc_export(self.ctx, ptr, h))
+        return h.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._check(self.lib.crt_ipc_open(self.ctx, handle, C.byref(p)))
+        return p.value
+
+    def restir_reserve(self, W, H):
+        p = C.c_void_p()
+        self._check(self.lib.crt_restir_reserve(self.ctx, W, H, C.byref(p)))
+        return p.value
+
+    def slab_set_links(self, links):
+        self._check(self.lib.crt_slab_set_links(self.ctx, C.byref(links) if links is not None else None))
+
+    def slab_exchange(self, W, H, which, with_class_plane, bufs):
+        self._check(self.lib.crt_slab_exchange(self.ctx, W, H, which, 1 if with_class_plane else 0, C.byref(bufs)))
 
     def launch(self, name, *args):
         """Shader::launch(name, ShaderArgument...) (shader.hpp:179-199): args are ctypes values / structures;

@@ -25,22 +25,38 @@ def slab_rows(H, world, rank, align=8):
     return edges[rank], edges[rank + 1]
 
 
-def weighted_slab_rows(row_cost, world, align=8):
-    """slab edges that balance a per-row cost estimate (e.g. last frame's per-row ray counts) instead of row counts;
-    returns the list of world + 1 edges"""
+def weighted_slab_rows(row_cost, world, align=8, min_rows=0):
+    """slab edges that balance a per-row cost estimate (e.g. measured slab times spread over their rows) instead
+    of row counts; every slab gets at least `min_rows` rows; returns the list of world + 1 edges"""
     H = len(row_cost)
     total = float(sum(row_cost))
     edges, acc, r = [0], 0.0, 1
     for y, c in enumerate(row_cost):
         acc += c
         while r < world and acc >= total * r / world:
-            e = min(H, max(edges[-1], (y + 1 + align - 1) // align * align))
+            e = min(H, max(edges[-1] + min_rows, (y + 1 + align - 1) // align * align))
             edges.append(e)
             r += 1
     while len(edges) < world:
         edges.append(H)
     edges.append(H)
+    # leave room for the slabs below: the last ones must keep min_rows too
+    for i in range(world - 1, 0, -1):
+        edges[i] = min(edges[i], edges[i + 1] - min_rows)
+    for i in range(1, world):
+        edges[i] = max(edges[i], edges[i - 1] + min_rows) // align * align
     return edges
+
+
+def rebalance(edges, slab_ms, align=8, min_rows=0):
+    """new edges from the measured compute time of every slab: the cost of a slab is spread evenly over its rows"""
+    H, world = edges[-1], len(edges) - 1
+    cost = [0.0] * H
+    for r in range(world):
+        rows = edges[r + 1] - edges[r]
+        for y in range(edges[r], edges[r + 1]):
+            cost[y] = slab_ms[r] / max(rows, 1)
+    return weighted_slab_rows(cost, world, align, min_rows)
 
 
 def halo_plan(H, edges, rank, halo=HALO):
@@ -100,3 +116,187 @@ def exchange(dist, tensor, W, H, layout, plan):
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     return sent
+
+
+class CudaArrayView:
+    """device memory owned by libcedecrt as a torch tensor (zero-copy, __cuda_array_interface__)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class SlabRenderer:
+    """The frame loop over one GPU's row slab.  Buffers are full-size (pixel indices stay global) and are torch
+    tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
+
+    def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True, edges=None, options=None, p2p=True):
+        """p2p: in fused mode with more than one rank, exchange halo rows by direct peer stores (csrc/slab_p2p.cu,
+        buffers shared through cudaIpc handles) instead of NCCL send/recv; needs slabs >= HALO rows, W % 16 == 0"""
+        import numpy as np
+
+        import cedecrt
+
+        self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
+        self.c, self.fused = cedecrt, fused
+        self.rt = cedecrt.Runtime(torch.cuda.current_device())
+        assert torch.cuda.current_stream().cuda_stream != 0, "bench needs a non-default torch stream"
+        self.rt.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.edges = edges if edges is not None else [slab_rows(H, world, r)[0] for r in range(world)] + [H]
+        self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
+        self.plan = halo_plan(H, self.edges, rank) if world > 1 else []
+        self.rt.set_row_range(self.y0, self.y1)
+        self.options = options or cedecrt.Options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+        self.eye = tuple(float(np.float32(v)) for v in cam[0])
+        self.raygen = cedecrt.lookat(cam[0], cam[1], W, H)
+        n = W * H
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        heights = [b - a for a, b in zip(self.edges, self.edges[1:])]
+        self.p2p = bool(p2p and fused and world > 1 and W % 16 == 0 and min(heights) >= HALO)
+        self._owned = []
+
+        def tbuf(nbytes, dtype, count, zero=False, shared=False):
+            if shared and self.p2p:  # cudaMalloc'ed by the library, so that it can be exported with cudaIpc
+                b = self.rt.buffer(dtype, count)
+                if zero:
+                    b.zero()
+                self._owned.append(b)
+                return torch.as_tensor(CudaArrayView(b.ptr, nbytes), device=dev), b
+            t = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
+            return t, self.rt.wrap(t.data_ptr(), dtype, count)
+
+        self.t_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).to(dev)
+        self.triangles = self.rt.wrap(self.t_tris.data_ptr(), cedecrt.TRIANGLE, len(tris))
+        lights = cedecrt.light_indices(tris)
+        self.t_lights = torch.from_numpy(lights.view(np.uint8)).to(dev)
+        self.lights = self.rt.wrap(self.t_lights.data_ptr(), np.uint32, len(lights))
+        self.n_tris, self.n_lights = len(tris), len(lights)
+        self.geom = self.rt.build_geometry(self.triangles)
+        self.t_pix, self.pixels = tbuf(4 * n, np.uint8, 4 * n)
+        self.t_acc, self.accumulation = tbuf(16 * n, cedecrt.FLOAT4, n, zero=True)
+        self.t_vis, self.visibility = tbuf(16 * n, cedecrt.VISIBILITY, n, zero=True)
+        self.t_r0, self.reservoir0 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True, shared=True)
+        self.t_r1, self.reservoir1 = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True, shared=True)
+        self.t_tmp, self.temporal = tbuf(76 * n, cedecrt.RESERVOIR, n, zero=True, shared=True)
+        self.bufs = self.rt.restir_buffers(self.pixels, self.accumulation, self.visibility, self.reservoir0,
+                                           self.reservoir1, self.temporal)
+        self.host_pixels = torch.empty(4 * W * (self.y1 - self.y0), dtype=torch.uint8).pin_memory()
+        self.frame_index = 0
+        self.t_cls = None
+        self.halo_bytes = 0
+        if self.p2p:
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """share the reservoir buffers, the pixel-class plane and a flag buffer with the adjacent ranks"""
+        import ctypes as C
+
+        rt, n = self.rt, self.W * self.H
+        scratch = rt.restir_reserve(self.W, self.H)
+        self._flags = rt.buffer("u1", 16).zero()
+        rt.sync()
+        mine = {"temporal": rt.ipc_export(self.temporal.ptr), "reservoir0": rt.ipc_export(self.reservoir0.ptr),
+                "reservoir1": rt.ipc_export(self.reservoir1.ptr), "scratch": rt.ipc_export(scratch),
+                "flags": rt.ipc_export(self._flags.ptr)}
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine)
+        links = self.c.SlabLinks()
+        links.my_flags = self._flags.ptr
+        for side, peer in (("up", self.rank - 1), ("down", self.rank + 1)):
+            if peer < 0 or peer >= self.world:
+                continue
+            h = everyone[peer]
+            ptrs = [rt.ipc_open(h[k]) for k in ("temporal", "reservoir0", "reservoir1")]
+            ptrs.append(rt.ipc_open(h["scratch"]) + 24 * n)
+            flags = rt.ipc_open(h["flags"])
+            getattr(links, side)[:] = (C.c_void_p * 4)(*ptrs)
+            # I am the peer's "down" neighbour if it is above me, so I raise its slot 1; and vice versa
+            setattr(links, side + "_flag", flags + (8 if side == "up" else 0))
+        rt.slab_set_links(links)
+        self.dist.barrier()  # nobody starts rendering before every rank has opened its neighbours' buffers
+
+    def set_edges(self, edges):
+        """move the slab boundaries (before any frame whose history matters: see calibrate)"""
+        self.edges = list(edges)
+        self.y0, self.y1 = self.edges[self.rank], self.edges[self.rank + 1]
+        self.plan = halo_plan(self.H, self.edges, self.rank) if self.world > 1 else []
+        self.rt.set_row_range(self.y0, self.y1)
+        self.host_pixels = self.torch.empty(4 * self.W * max(self.y1 - self.y0, 1), dtype=self.torch.uint8).pin_memory()
+
+    def reset_history(self):
+        for t in (self.t_tmp, self.t_r0, self.t_r1, self.t_acc):
+            t.zero_()
+        self.frame_index = 0
+
+    def calibrate(self, rounds=2, frames=2):
+        """Load balancing for a static camera: render a few throw-away frames, measure every slab's own kernel time
+        (waiting for neighbours excluded), move the boundaries so that the times even out, repeat; then clear the
+        history so that the real sequence starts at frame 1 with the final partition.  Returns the edges."""
+        if self.world == 1:
+            return self.edges
+        torch, dist = self.torch, self.dist
+        for _ in range(rounds):
+            self.reset_history()
+            self.frame()  # first frame has no temporal history: not representative
+            self.rt.profile_begin()
+            for _ in range(frames):
+                self.frame()
+            marks = self.rt.profile_end()
+            mine = sum(ms for name, ms in marks if name != "signal_wait") / frames
+            t = torch.zeros(self.world, dtype=torch.float64, device="cuda")
+            t[self.rank] = mine
+            dist.all_reduce(t)
+            new_edges = rebalance(self.edges, [float(x) for x in t.tolist()], 8, HALO + 9 if self.p2p else 8)
+            self.set_edges(new_edges)
+        self.reset_history()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return self.edges
+
+    def _rows(self, t, elem, a, b):
+        return t[(self.H - b) * self.W * elem:(self.H - a) * self.W * elem]
+
+    def exchange(self, t, layout):
+        if self.world > 1:
+            self.halo_bytes += exchange(self.dist, t, self.W, self.H, layout, self.plan)
+
+    def frame(self):
+        rt, W, H, o, g, t, v, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.visibility, self.eye
+        self.frame_index += 1
+        f = self.frame_index
+        if self.fused and self.p2p:
+            rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
+            for k in range(o.spatial_resampling_passes):  # input of pass k: temporal, reservoir1, reservoir0, ...
+                rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), k == 0, self.bufs)
+                rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
+            rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
+            return
+        if self.fused:
+            rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
+            if self.world > 1:
+                if self.t_cls is None:
+                    self.t_cls = self.torch.as_tensor(CudaArrayView(rt.restir_class_plane(), W * H), device="cuda")
+                self.exchange(self.t_cls, CLASS_PLANE)
+            for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
+                self.exchange(self.t_tmp if k == 0 else (self.t_r1 if k % 2 else self.t_r0), SOA_RESERVOIR)
+                rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
+            rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
+            return
+        rt.raycast(W, H, g, t, self.raygen, v)
+        self.exchange(self.t_vis, AOS_VISIBILITY)
+        rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
+        rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        rt.save_temporal_reservoir(W, H, self.reservoir0, self.temporal)
+        bi, bo, ti = self.reservoir0, self.reservoir1, self.t_r0
+        for k in range(o.spatial_resampling_passes):
+            if k != 0:
+                bi, bo = bo, bi
+                ti = self.t_r1 if ti is self.t_r0 else self.t_r0
+            self.exchange(ti, AOS_RESERVOIR)
+            rt.spatial_resampling(W, H, f, k, g, t, v, eye, o, bi, bo)
+        rt.resolve(self.accumulation, W, H, g, t, v, eye, o, bo)
+        rt.tone_mapping(self.pixels, self.accumulation, W, H)
+
+    def download_pixels(self):
+        src = self._rows(self.t_pix, 4, self.y0, self.y1)
+        self.host_pixels.copy_(src, non_blocking=True)

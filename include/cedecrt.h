@@ -218,6 +218,36 @@ int crt_restir_class_plane(crt_ctx* ctx, void** out);
 int crt_reservoir_export_aos(crt_ctx* ctx, int width, int height, crt_buffer soa_storage, crt_buffer aos_out);
 int crt_reservoir_import_aos(crt_ctx* ctx, int width, int height, crt_buffer aos_in, crt_buffer soa_storage);
 
+/* ---- multi-GPU row slabs: halo rows by direct peer stores (new; the reference is single-GPU).
+ * One process per GPU.  Each rank allocates its three reservoir buffers with crt_malloc, calls
+ * crt_restir_reserve, exports both with crt_ipc_export (cudaIpc handles, 64 bytes, to be passed to the neighbour
+ * ranks by any host channel), opens its neighbours' handles and registers the peer pointers with
+ * crt_slab_set_links.  crt_slab_exchange then replaces the host-side halo exchange between the stages of the fused
+ * frame: it stores this rank's 87 boundary rows of the chosen buffer into the neighbours' buffers over NVLink,
+ * signals them, and waits for their rows (csrc/slab_p2p.cu).  Slabs must be at least 87 rows tall and the image
+ * width a multiple of 16; otherwise exchange the rows on the host side (python/slabs.py does it with NCCL). */
+int crt_ipc_export(crt_ctx* ctx, void* device_ptr, unsigned char handle_out[64]);
+int crt_ipc_open(crt_ctx* ctx, const unsigned char handle[64], void** peer_ptr_out);
+int crt_ipc_close(crt_ctx* ctx, void* peer_ptr);
+/* allocates the fused frame's per-pixel scratch for a W x H image now (instead of at the first frame) and returns
+ * the base of that allocation; the pixel-class plane is the W*H bytes at offset 24*W*H */
+int crt_restir_reserve(crt_ctx* ctx, int width, int height, void** scratch_base_out);
+typedef struct
+{
+    /* peer pointers into the slab above (smaller yi) / below: [0] temporal, [1] reservoir0, [2] reservoir1 storage,
+     * [3] pixel-class plane; all NULL = no neighbour on that side */
+    void* up[4];
+    void* down[4];
+    void* up_flag;   /* 8-byte slot this rank raises in the upper neighbour's flag buffer (its slot 1) */
+    void* down_flag; /* ... in the lower neighbour's flag buffer (its slot 0) */
+    void* my_flags;  /* this rank's own flag buffer: 16 zeroed bytes; slot 0 is raised by `up`, slot 1 by `down` */
+} crt_slab_links;
+int crt_slab_set_links(crt_ctx* ctx, const crt_slab_links* links);
+/* which: 0 temporal, 1 reservoir0, 2 reservoir1 (the input of the next spatial pass); with_class_plane: also
+ * send the pixel-class rows (once per frame, after crt_restir_frame_begin) */
+int crt_slab_exchange(crt_ctx* ctx, int width, int height, int which, int with_class_plane,
+                      const crt_restir_buffers* buffers);
+
 /* Shader::launch call shape (common/shader.hpp:179-199): kernel by name, params as the void*[] that
  * ShaderArgument builds (pointers to by-value arguments, in order), grid/block accepted and ignored.
  * Names: raycast, generate_candidate, temporal_resampling, save_temporal_reservoir, spatial_resampling,
