@@ -28,20 +28,20 @@ namespace crt
 template <class L, int MODE>
 __global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
     k_candidate_temporal(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
-                         L lights, crt_options options, SoaStore temporal, GBuf g, ShadowQueue q)
+                         L lights, crt_options options, SoaStore temporal, GBuf g, ShadowQueue q, HaloPeers peers)
 {
     const TilePix t = this_pixel(W, H, rows);
     DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
-    if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, lights, make_opt(options), temporal, g);
+    if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, lights, make_opt(options), temporal, g, peers);
     queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
 }
 template <int MODE>
 __global__ void __launch_bounds__(256)
     k_spatial_fast(int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye, crt_options options, SoaStore in,
-                   SoaStore out, GBuf g)
+                   SoaStore out, GBuf g, HaloPeers peers)
 {
     const TilePix t = this_pixel(W, H, rows);
-    if (t.in) px_spatial_fast<Math<MODE>>(t.px, W, H, frame, pass, bvh, eye, make_opt(options), in, out, g);
+    if (t.in) px_spatial_fast<Math<MODE>>(t.px, W, H, frame, pass, bvh, eye, make_opt(options), in, out, g, peers);
 }
 __global__ void __launch_bounds__(256)
     k_resolve_fast(crt_float4* accum, int W, int H, Rows rows, const float* tris60,
@@ -107,6 +107,25 @@ int check_buffers(int W, int H, const crt_restir_buffers* b)
                 "the three reservoir buffers must be distinct");
     return CRT_OK;
 }
+// the neighbours' copies of reservoir buffer `which` (0 temporal, 1 reservoir0, 2 reservoir1) for kernels that
+// mirror their boundary rows (crt_slab_set_links with slabs at least kHaloRows tall); empty otherwise
+HaloPeers halo_peers(const crt_ctx* ctx, int which, Rows rows, bool with_class, size_t n)
+{
+    HaloPeers p;
+    if (!ctx->links_set || rows.y1 - rows.y0 < kHaloRows) return p;
+    p.up = (char*)ctx->links.up[which];
+    p.down = (char*)ctx->links.down[which];
+    if (with_class)
+    {
+        p.up_cls = (uint8_t*)ctx->links.up[3];
+        p.down_cls = (uint8_t*)ctx->links.down[3];
+    }
+    p.up_end = rows.y0 + kHaloRows;
+    p.down_begin = rows.y1 - kHaloRows;
+    (void)n;
+    return p;
+}
+int which_of(const crt_restir_buffers* b, const crt_buffer& x) { return x.data == b->temporal.data ? 0 : x.data == b->reservoir0.data ? 1 : 2; }
 // input and output of spatial pass k in fused mode
 void pass_buffers(const crt_restir_buffers* b, int pass, crt_buffer* in, crt_buffer* out)
 {
@@ -168,6 +187,7 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     const SoaStore T = soa(b->temporal, n);
     const dim3 grid = tile_grid(W, rows);
     const bool exact = ctx->math_mode == CRT_MATH_EXACT;
+    const HaloPeers peers = halo_peers(ctx, 0, rows, true, n);
     if (ctx->light_table)
     {
         const LightRec* table = nullptr;
@@ -175,17 +195,22 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
         if (rc != CRT_OK) return rc;
         const LightsTable L{table, n_lights};
         auto k = exact ? k_candidate_temporal<LightsTable, 1> : k_candidate_temporal<LightsTable, 0>;
-        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q);
+        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q, peers);
     }
     else
     {
         const LightsIndexed L{tris60, (const uint32_t*)lights.data, n_lights};
         auto k = exact ? k_candidate_temporal<LightsIndexed, 1> : k_candidate_temporal<LightsIndexed, 0>;
-        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q);
+        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q, peers);
     }
     rc = check_launch(ctx, "candidate_temporal");
     if (rc != CRT_OK || !options.use_visibility_reuse) return rc;
-    return queue_trace<kEpiSoaVisibility>(ctx, geom, q, ShadowSink{nullptr, nullptr, 0, (uint32_t*)T.plane(2, 0)});
+    ShadowSink sink{nullptr, nullptr, 0, (uint32_t*)T.plane(2, 0)};
+    if (peers.up) sink.up_plane2 = (uint32_t*)SoaStore{peers.up, n}.plane(2, 0);
+    if (peers.down) sink.down_plane2 = (uint32_t*)SoaStore{peers.down, n}.plane(2, 0);
+    sink.up_first_idx = (uint32_t)((size_t)(H - peers.up_end) * W);        // rows yi < up_end
+    sink.down_end_idx = (uint32_t)((size_t)(H - peers.down_begin) * W);    // rows yi >= down_begin
+    return queue_trace<kEpiSoaVisibility>(ctx, geom, q, sink);
 }
 
 extern "C" int crt_restir_spatial_pass(crt_ctx* ctx, int W, int H, int frame, int pass, crt_geometry geom,
@@ -212,7 +237,9 @@ extern "C" int crt_restir_spatial_pass(crt_ctx* ctx, int W, int H, int frame, in
     crt_buffer in, out;
     pass_buffers(b, pass, &in, &out);
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_spatial_fast<1> : k_spatial_fast<0>;
-    k<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(W, H, rows, frame, pass, geom->view(), to_f3(eye), options, soa(in, n), soa(out, n), g);
+    // the last pass's output is only read by this rank's resolve: nothing to mirror
+    const HaloPeers peers = pass + 1 < options.spatial_resampling_passes ? halo_peers(ctx, which_of(b, out), rows, false, n) : HaloPeers();
+    k<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(W, H, rows, frame, pass, geom->view(), to_f3(eye), options, soa(in, n), soa(out, n), g, peers);
     return check_launch(ctx, "spatial_fast");
 }
 

@@ -137,6 +137,28 @@ struct GBuf
     }
 };
 
+// Multi-GPU row slabs (slab_p2p.cu): the neighbouring slabs' copies of the buffer a kernel writes.  A pixel whose
+// row lies within kHaloRows of the slab boundary is stored there too — the halo rows travel over NVLink from the
+// producing kernel's own epilogue, overlapped with the rest of the kernel, instead of in a copy afterwards.
+struct HaloPeers
+{
+    char* up = nullptr;         // reservoir storage of the slab above (rows yi < up_end are mirrored there)
+    char* down = nullptr;       // ... of the slab below (rows yi >= down_begin)
+    uint8_t* up_cls = nullptr;  // pixel-class planes (candidate kernel only)
+    uint8_t* down_cls = nullptr;
+    int up_end = 0, down_begin = 0;
+    CRT_HD void mirror(const Pix& px, size_t n, const Res& r) const
+    {
+        if (up && px.yi < up_end) SoaStore{up, n}.store(px.idx, r);
+        if (down && px.yi >= down_begin) SoaStore{down, n}.store(px.idx, r);
+    }
+    CRT_HD void mirror_class(const Pix& px, uint8_t c) const
+    {
+        if (up_cls && px.yi < up_end) up_cls[px.idx] = c;
+        if (down_cls && px.yi >= down_begin) down_cls[px.idx] = c;
+    }
+};
+
 // ---- generate_candidate (10_restir_di.cu:36-135) + temporal_resampling (:137-237) + save (:239-254).
 // `temporal` holds last frame's post-temporal reservoirs on entry and this frame's on exit.
 // Requires !opt.shadowed (the fused frame falls back to the per-kernel path otherwise).
@@ -145,7 +167,7 @@ struct GBuf
 template <class M, class L>
 CRT_HD DeferredRay px_candidate_temporal(const Pix& px, int frame, const Bvh& bvh, const float* tris60,
                                          const crt_visibility* vis, f3 eye, const L& lights, const Opt& opt_in,
-                                         const SoaStore& temporal, const GBuf& g)
+                                         const SoaStore& temporal, const GBuf& g, const HaloPeers& peers = HaloPeers())
 {
     Opt opt = opt_in;
     opt.shadowed = false;  // compile-time constant here: no traversal code inside the target function
@@ -161,10 +183,12 @@ CRT_HD DeferredRay px_candidate_temporal(const Pix& px, int frame, const Bvh& bv
     if (skip)
     {
         g.cls[px.idx] = kPixSkip;
+        peers.mirror_class(px, kPixSkip);     // (the reservoirs of skipped pixels are never read by a neighbour)
         temporal.store(px.idx, empty_res());  // what the reference leaves there: Reservoir{} copied by save_temporal
         return ray;
     }
     g.cls[px.idx] = kPixDiffuse;
+    peers.mirror_class(px, kPixDiffuse);
     Pcg rng(hash_pcg4(px.xi, px.yi, frame, 0), 0);
     const Surf surf = surface_from_visibility(tri, v.u, v.v, eye);
     g.store(px.idx, surf);
@@ -178,6 +202,7 @@ CRT_HD DeferredRay px_candidate_temporal(const Pix& px, int frame, const Bvh& bv
     }
     if (opt.reuse && candidate_survives) ray = visibility_ray(surf.p, surf.n, r.s.hp);
     temporal.store(px.idx, r);
+    peers.mirror(px, temporal.n, r);  // visibility still pending for a deferred ray: the tracer mirrors the final word
     return ray;
 }
 
@@ -185,7 +210,7 @@ CRT_HD DeferredRay px_candidate_temporal(const Pix& px, int frame, const Bvh& bv
 // fused frame skips)
 template <class M>
 CRT_HD void px_spatial_fast(const Pix& px, int W, int H, int frame, int pass, const Bvh& bvh, f3 eye, const Opt& opt_in,
-                            const SoaStore& in, const SoaStore& out, const GBuf& g)
+                            const SoaStore& in, const SoaStore& out, const GBuf& g, const HaloPeers& peers = HaloPeers())
 {
     Opt opt = opt_in;
     opt.shadowed = false;
@@ -205,6 +230,7 @@ CRT_HD void px_spatial_fast(const Pix& px, int W, int H, int frame, int pass, co
     }
     r.ucw = ucw_of(r, target_function(bvh, surf.p, surf.n, r.s.hp, r.s.hn, r.s.rad, false));
     out.store(px.idx, r);
+    peers.mirror(px, out.n, r);
 }
 
 // ---- resolve (10_restir_di.cu:390-459).  Sky/emissive pixels are finished here; for the others the shadow ray

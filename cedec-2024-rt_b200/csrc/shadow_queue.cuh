@@ -76,6 +76,11 @@ struct ShadowSink
     crt_float4* accumulation;   // kEpiResolve*
     int accumulate;
     uint32_t* soa_plane2;       // kEpiSoaVisibility: plane 2 of the SoA reservoir buffer (M | visibility << 31 in word 2)
+    // multi-GPU slabs: plane 2 of the neighbours' copies; pixel indices below up_end_idx belong... see HaloPeers.
+    // Bottom-up storage: rows yi < up_end are the pixel indices >= up_first_idx, rows yi >= down_begin those < down_end_idx
+    uint32_t* up_plane2 = nullptr;
+    uint32_t* down_plane2 = nullptr;
+    uint32_t up_first_idx = 0, down_end_idx = 0;
 };
 
 // the shading factors stay in the queue record until the ray is decided (keeps the walk's register count down)
@@ -91,7 +96,13 @@ __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const Sh
     else if (EPI == kEpiSoaVisibility)
     {
         // the reservoir was stored with visibility = false; only this thread touches the word now
-        if (!occluded) sink.soa_plane2[(size_t)pix * 4 + 2] |= kVisBit;
+        if (!occluded)
+        {
+            const uint32_t w = sink.soa_plane2[(size_t)pix * 4 + 2] | kVisBit;
+            sink.soa_plane2[(size_t)pix * 4 + 2] = w;
+            if (sink.up_plane2 && pix >= sink.up_first_idx) sink.up_plane2[(size_t)pix * 4 + 2] = w;
+            if (sink.down_plane2 && pix < sink.down_end_idx) sink.down_plane2[(size_t)pix * 4 + 2] = w;
+        }
     }
     else
     {

@@ -1,11 +1,12 @@
 // slab_p2p.cu — halo exchange between the row slabs of one node by direct peer stores over NVLink.
 //
 // New with respect to the reference (single GPU).  Each rank owns image rows [y0, y1) of full-size buffers
-// (crt_set_row_range).  After a stage that produced reservoir rows, crt_slab_exchange
-//   1. copies the kHaloRows boundary rows of the stage's planar reservoir buffer (and, once per frame, of the
-//      pixel-class plane) straight into the neighbours' buffers — peer pointers obtained with cudaIpc
-//      (crt_ipc_export / crt_ipc_open), so the bytes cross NVLink/NVSwitch once, written by the producer,
-//      with no staging buffer and no NCCL launch;
+// (crt_set_row_range).  The kernels of the fused frame that produce reservoir rows store the kHaloRows boundary
+// rows into the neighbours' buffers as well (restir_fast.cuh: HaloPeers — peer pointers obtained with cudaIpc,
+// crt_ipc_export / crt_ipc_open), so the bytes cross NVLink/NVSwitch once, from the producing kernel's epilogue,
+// overlapped with the rest of that kernel, with no staging buffer and no NCCL launch.  crt_slab_exchange then
+//   1. (only with push_rows != 0, e.g. for buffers written by other means) copies the boundary rows with a
+//      dedicated kernel;
 //   2. raises a monotonically increasing counter in each neighbour's flag slot (release at system scope);
 //   3. waits (one spinning thread) until both neighbours have raised this rank's slots to the same count.
 // Step 3 is the only synchronisation: a neighbour's flag for stage s also proves that it finished every earlier
@@ -105,8 +106,9 @@ extern "C" int crt_slab_set_links(crt_ctx* ctx, const crt_slab_links* links)
     return CRT_OK;
 }
 
-extern "C" int crt_slab_exchange(crt_ctx* ctx, int W, int H, int which, int with_class_plane, const crt_restir_buffers* b)
+extern "C" int crt_slab_exchange(crt_ctx* ctx, int W, int H, int which, int push_rows, const crt_restir_buffers* b)
 {
+    const int with_class_plane = push_rows > 1;
     CRT_REQUIRE(ctx && b, "null argument");
     CRT_REQUIRE(ctx->links_set, "crt_slab_set_links has not been called");
     CRT_REQUIRE(which >= 0 && which < 3, "which: 0 temporal, 1 reservoir0, 2 reservoir1");
@@ -144,8 +146,8 @@ extern "C" int crt_slab_exchange(crt_ctx* ctx, int W, int H, int which, int with
     };
     CRT_REQUIRE(((size_t)W * halo) % 16 == 0 || !with_class_plane, "class-plane rows must be 16-byte multiples");
     CRT_REQUIRE(!with_class_plane || (ctx->gbuf && ctx->gbuf_pixels == n), "crt_restir_reserve(W, H) must precede the exchange");
-    if (has_up) add_rows((char*)L.up[which], (char*)L.up[3], rows.y0, rows.y0 + halo);
-    if (has_down) add_rows((char*)L.down[which], (char*)L.down[3], rows.y1 - halo, rows.y1);
+    if (push_rows && has_up) add_rows((char*)L.up[which], (char*)L.up[3], rows.y0, rows.y0 + halo);
+    if (push_rows && has_down) add_rows((char*)L.down[which], (char*)L.down[3], rows.y1 - halo, rows.y1);
     if (nseg)
     {
         const unsigned bx = (unsigned)((max16 + 255) / 256 < (size_t)ctx->sm_count * 2 ? (max16 + 255) / 256 : (size_t)ctx->sm_count * 2);

@@ -473,8 +473,8 @@ class Runtime:
     def slab_set_links(self, links):
         self._check(self.lib.crt_slab_set_links(self.ctx, C.byref(links) if links is not None else None))
 
-    def slab_exchange(self, W, H, which, with_class_plane, bufs):
-        self._check(self.lib.crt_slab_exchange(self.ctx, W, H, which, 1 if with_class_plane else 0, C.byref(bufs)))
+    def slab_exchange(self, W, H, which, bufs, push_rows=0):
+        self._check(self.lib.crt_slab_exchange(self.ctx, W, H, which, push_rows, C.byref(bufs)))
 
     def launch(self, name, *args):
         """Shader::launch(name, ShaderArgument...) (shader.hpp:179-199): args are ctypes values / structures;

@@ -267,7 +267,7 @@ class SlabRenderer:
         if self.fused and self.p2p:
             rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
             for k in range(o.spatial_resampling_passes):  # input of pass k: temporal, reservoir1, reservoir0, ...
-                rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), k == 0, self.bufs)
+                rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), self.bufs)  # rows were mirrored by the kernels
                 rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
             rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
             return

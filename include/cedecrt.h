@@ -243,9 +243,12 @@ typedef struct
     void* my_flags;  /* this rank's own flag buffer: 16 zeroed bytes; slot 0 is raised by `up`, slot 1 by `down` */
 } crt_slab_links;
 int crt_slab_set_links(crt_ctx* ctx, const crt_slab_links* links);
-/* which: 0 temporal, 1 reservoir0, 2 reservoir1 (the input of the next spatial pass); with_class_plane: also
- * send the pixel-class rows (once per frame, after crt_restir_frame_begin) */
-int crt_slab_exchange(crt_ctx* ctx, int width, int height, int which, int with_class_plane,
+/* Call between the stages of the fused frame, before the spatial pass that reads buffer `which` (0 temporal,
+ * 1 reservoir0, 2 reservoir1).  While links are set, crt_restir_frame_begin / crt_restir_spatial_pass already
+ * mirror their boundary rows into the neighbours' buffers, so push_rows = 0 only signals the neighbours and waits
+ * for theirs; push_rows = 1 first copies the 87 boundary rows of the buffer with a dedicated kernel, 2 also the
+ * pixel-class rows (for buffers filled by other means). */
+int crt_slab_exchange(crt_ctx* ctx, int width, int height, int which, int push_rows,
                       const crt_restir_buffers* buffers);
 
 /* Shader::launch call shape (common/shader.hpp:179-199): kernel by name, params as the void*[] that
