@@ -145,17 +145,20 @@ __device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, const 
 }
 
 constexpr int kShadowWarps = 4;    // warps per block of the persistent kernel
-constexpr int kPairCap = 128;      // (ray, triangle) pairs a warp tests per cooperative round trip
 
 // Persistent any-hit walk over the queue.  Launch with (resident blocks per SM) x (SM count) blocks.
 //
 // Each iteration has two warp-wide phases:
 //   node phase      every walking lane takes one node step of its own ray (8 child boxes);
 //   triangle phase  the (ray, triangle) pairs the node steps produced — a few lanes own a few triangles each —
-//                   are pooled in shared memory and dealt out evenly to all 32 lanes; a lane tests a triangle
-//                   against the *owner's* ray (fetched with shuffles) and reports an occlusion by setting the
-//                   owner's bit.  Without pooling the ~100-instruction triangle test ran with 3 of 32 lanes
-//                   (profiles/r1/source_c_trace_shadow_queue.txt).
+//                   are dealt out evenly to all 32 lanes: pair g belongs to the lane whose running pair count
+//                   first exceeds g (a five-step binary search over the warp's inclusive scan, by shuffles), the
+//                   lane picks the owner's (g - first pair)-th triangle, tests it against the *owner's* ray
+//                   (fetched with shuffles) and the owners read the outcome of their pairs from one ballot.
+//                   Everything stays in registers: no shared memory, no atomics.  (Without pooling the
+//                   ~100-instruction triangle test ran with 3 of 32 lanes, profiles/r1/source_c_*; the first pooled
+//                   form published pairs through shared memory with a per-lane loop that cost 19 % of the kernel's
+//                   instructions at 7 lanes each, profiles/r1/lines_k_k_trace_shadow_queue_1.txt.)
 // A lane whose ray is decided takes the next ray from the global counter as soon as fewer than
 // kRefillThreshold lanes of its warp are still walking.
 #ifndef CRT_SHADOW_MINBLOCKS
@@ -164,14 +167,9 @@ constexpr int kPairCap = 128;      // (ray, triangle) pairs a warp tests per coo
 template <int EPI>
 __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_trace_shadow_queue(Bvh bvh, ShadowQueue q, ShadowSink sink)
 {
-    __shared__ uint32_t s_pairs[kShadowWarps][kPairCap];
-    __shared__ uint32_t s_occluded[kShadowWarps];
     const uint32_t n_rays = *q.count;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    uint32_t* pairs = s_pairs[warp];
-    if (lane == 0) s_occluded[warp] = 0u;
-    __syncwarp();
 
     bool active = false, exhausted = false;
     RaySetup r;
@@ -219,8 +217,9 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
             // node phase
             bool missed = false;
             if (active) missed = !shadow_node_step(bvh, w, r);
-            // triangle phase: pool the pairs of the whole warp
-            const uint32_t cnt = active ? (uint32_t)__popc(w.tmask) : 0u;
+            // triangle phase: inclusive scan of the per-lane pair counts
+            const uint32_t own_mask = active ? w.tmask : 0u;
+            const uint32_t cnt = (uint32_t)__popc(own_mask);
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1)
@@ -229,70 +228,54 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                 if (lane >= d) incl += v;
             }
             const uint32_t total = __shfl_sync(full, incl, 31);
-            uint32_t pos = incl - cnt;  // this lane's first pair
-            for (uint32_t chunk = 0; chunk < total; chunk += kPairCap)
+            const uint32_t excl = incl - cnt;  // this lane's first pair
+            bool occluded = false;
+            for (uint32_t base = 0; base < total; base += 32)
             {
-                // owners publish (owner lane, triangle record) for the pairs that fall into this chunk
-                uint32_t m = w.tmask;
-                uint32_t p = pos;
-                while (m && p < chunk + kPairCap)
+                const uint32_t g = base + (uint32_t)lane;  // the pair this lane tests
+                int owner = 0;                             // = number of lanes whose pairs all lie before g
+#pragma unroll
+                for (int step = 16; step; step >>= 1)
                 {
-                    const int i = __ffs((int)m) - 1;
-                    if (p >= chunk)
-                    {
-                        pairs[p - chunk] = ((uint32_t)lane << 27) | (w.tri_base + (uint32_t)i);
-                        m &= m - 1u;
-                        ++p;
-                    }
-                    else
-                    {
-                        m &= m - 1u;
-                        ++p;
-                    }
+                    const uint32_t v = __shfl_sync(full, incl, owner + step - 1);
+                    if (v <= g) owner += step;
                 }
-                // (pairs below `chunk` were handled in an earlier round: drop them from the owner's mask)
-                w.tmask = m;
-                pos = p;
-                __syncwarp();
-                const uint32_t n_here = min(total - chunk, (uint32_t)kPairCap);
-                for (uint32_t k0 = 0; k0 < n_here; k0 += 32)
+                const bool valid = g < total;
+                const uint32_t first = __shfl_sync(full, excl, owner);
+                uint32_t m = __shfl_sync(full, own_mask, owner);
+                const uint32_t tri_base = __shfl_sync(full, w.tri_base, owner);
+                RaySetup o;
+                o.ro.x = __shfl_sync(full, r.ro.x, owner);
+                o.ro.y = __shfl_sync(full, r.ro.y, owner);
+                o.ro.z = __shfl_sync(full, r.ro.z, owner);
+                o.rd.x = __shfl_sync(full, r.rd.x, owner);
+                o.rd.y = __shfl_sync(full, r.rd.y, owner);
+                o.rd.z = __shfl_sync(full, r.rd.z, owner);
+                bool hit = false;
+                if (valid)
                 {
-                    const uint32_t k = k0 + (uint32_t)lane;
-                    const bool valid = k < n_here;
-                    const uint32_t pr = valid ? pairs[k] : ((uint32_t)lane << 27);
-                    const int owner = (int)(pr >> 27);
-                    RaySetup o;
-                    o.ro.x = __shfl_sync(full, r.ro.x, owner);
-                    o.ro.y = __shfl_sync(full, r.ro.y, owner);
-                    o.ro.z = __shfl_sync(full, r.ro.z, owner);
-                    o.rd.x = __shfl_sync(full, r.rd.x, owner);
-                    o.rd.y = __shfl_sync(full, r.rd.y, owner);
-                    o.rd.z = __shfl_sync(full, r.rd.z, owner);
-                    if (valid)
-                    {
-                        Hit h;
-                        h.prim = -1;
-                        h.t = 0.99f;
-                        h.u = h.v = 0.0f;
-                        if (intersect_wide_tri(bvh.tris + (pr & 0x07ffffffu), o, 0.0f, h))
-                            atomicOr(&s_occluded[warp], 1u << owner);
-                    }
+                    for (uint32_t k = g - first; k; --k) m &= m - 1u;  // drop the owner's earlier triangles
+                    Hit h;
+                    h.prim = -1;
+                    h.t = 0.99f;
+                    h.u = h.v = 0.0f;
+                    hit = intersect_wide_tri(bvh.tris + tri_base + (uint32_t)(__ffs((int)m) - 1), o, 0.0f, h);
                 }
-                __syncwarp();
+                // lanes [excl - base, incl - base) of this round tested this lane's pairs
+                const uint32_t hits = __ballot_sync(full, hit);
+                const int lo = (int)excl - (int)base, hi = (int)incl - (int)base;
+                if (hi > 0 && lo < 32)
+                {
+                    const uint32_t below_hi = hi >= 32 ? full : ((1u << hi) - 1u);
+                    const uint32_t below_lo = lo <= 0 ? 0u : ((1u << lo) - 1u);
+                    occluded |= (hits & below_hi & ~below_lo) != 0u;
+                }
             }
             w.tmask = 0;
-            const uint32_t occ = s_occluded[warp];
-            __syncwarp();
-            if (lane == 0) s_occluded[warp] = 0u;
-            __syncwarp();
-            if (active)
+            if (active && (occluded || missed))
             {
-                const bool occluded = (occ >> lane) & 1u;
-                if (occluded || missed)
-                {
-                    shadow_epilogue<EPI>(sink, q.rays + ray_idx, pix, occluded);
-                    active = false;
-                }
+                shadow_epilogue<EPI>(sink, q.rays + ray_idx, pix, occluded);
+                active = false;
             }
             act = __ballot_sync(full, active);
             if (act == 0) break;
