@@ -51,6 +51,7 @@ struct Bvh
     const WideNode* nodes;
     const WideTri* tris;
     float postpone_ratio;  // triangle-postponing threshold of the walk (0 = never postpone), see walk_step
+    uint32_t f32_one = 0x3f800000u;  // bits of 1.0f as a *run-time* value: see byte_to_unit_float
 };
 
 struct Hit
@@ -94,21 +95,64 @@ CRT_HD u4 load_u4(const void* p)
 #endif
 }
 
-// Quantised plane coordinate q (byte k of a word) as the float 1 + q * 2^-15: on the device a single PRMT drops
-// the byte into mantissa bits 8..15 of 1.0f — no integer-to-float conversion and no bias subtraction.
-// intersect_node folds the "1 +" and the 2^-15 into the per-node constants.
-CRT_HD float byte_to_unit_float(uint32_t w, int k)
+// 32 bytes in one request (sm_100: LDG.E.ENL2.256); p must be 32-byte aligned.  For the random 64-byte gathers of
+// the reservoir passes this halves the number of L1 tag lookups per record against 128-bit loads.
+struct u8w { u4 lo, hi; };
+CRT_HD u8w load_u8w(const void* p)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3f800000u, 0x7604 | (k << 4)));
+    u8w v;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v.lo.x), "=r"(v.lo.y), "=r"(v.lo.z), "=r"(v.lo.w), "=r"(v.hi.x), "=r"(v.hi.y), "=r"(v.hi.z), "=r"(v.hi.w)
+        : "l"(p));
+    return v;
 #else
-    return u2f(0x3f800000u | (((w >> (8 * k)) & 0xffu) << 8));
+    u8w v;
+    memcpy(&v, p, 32);
+    return v;
 #endif
 }
-// The folded form rounds (o - a * 2^15) once, an error of at most cell/512 in space; child boxes are therefore
-// quantised with a margin of kQuantMargin cells on every side (bvh_build.cuh: collapse_item), which keeps the
-// slab test conservative by construction.
-constexpr float kQuantMargin = 1.0f / 128.0f;
+
+// Quantised plane coordinate q (byte K of a word) as the float 1 + q * 2^-16, without an integer-to-float
+// conversion and without a bias subtraction: the byte is added, times 128, into the mantissa of 1.0f.
+// intersect_node folds the "1 +" and the 2^-16 into the per-node constants.
+//
+// On the device this is one IDP.4A (dp4a with the byte weights 128 << 8K and the accumulator 1.0f): it runs on the
+// FMA pipe, whose other load in the node test is 48 FFMAs at one issue cycle each, while the ALU pipe (two issue
+// cycles per warp instruction) already carries the 32 min/max, the compares and the hit-mask assembly.  The earlier
+// form — one PRMT per byte — put 48 more instructions on the ALU pipe, which ncu showed at 65 % utilisation against
+// 32 % for the FMA pipe (profiles/r1/ncu_m_*; pipe assignment and rates measured with profiles/microbench/pipes.cu:
+// PRMT 2.04, IDP.4A 2.03, FFMA 1.08 cycles; PRMT+IDP.4A overlap, IDP.4A+FFMA add up).
+// `one` is 0x3f800000 handed in as a run-time value (Bvh::f32_one, a kernel parameter) so that the compiler keeps
+// it in a register instead of re-materialising constants around every conversion.
+template <int K>
+CRT_HD float byte_to_unit_float(uint32_t w, uint32_t one)
+{
+#if defined(__CUDA_ARCH__)
+#if defined(CRT_NODE_PRMT)
+    uint32_t d;  // byte dropped into mantissa bits 8..15 by one PRMT: 1 + q * 2^-15 (kPlaneScale below follows)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(one), "n"(0x7604 | (K << 4)));
+    return __uint_as_float(d);
+#else
+    return __uint_as_float(__dp4a(w, 128u << (8 * K), one));
+#endif
+#else
+#if defined(CRT_NODE_PRMT)
+    return u2f(one | (((w >> (8 * K)) & 0xffu) << 8));
+#else
+    return u2f(one + (((w >> (8 * K)) & 0xffu) << 7));
+#endif
+#endif
+}
+#if defined(CRT_NODE_PRMT)
+constexpr float kPlaneScale = 32768.0f;
+#else
+constexpr float kPlaneScale = 65536.0f;
+#endif
+// The folded form rounds (o - a * kPlaneScale) once, an error of at most cell/256 in space (cell/512 for the PRMT
+// form); child boxes are therefore quantised with a margin of kQuantMargin cells on every side (bvh_build.cuh:
+// collapse_item), which keeps the slab test conservative by construction.
+constexpr float kQuantMargin = 1.0f / 64.0f;
 
 // test-only instrumentation (tests/emu with -DCRT_COUNT): per-thread node / triangle step counters
 #if defined(CRT_COUNT) && !defined(__CUDA_ARCH__)
@@ -162,8 +206,8 @@ CRT_HD uint32_t intersect_node(const Bvh& bvh, uint32_t node_idx, const RaySetup
                 sz = u2f(((e_imask >> 16) & 0xffu) << 23);
     const uint32_t imask = e_imask >> 24;
     // plane at q cells: t = (p + q*cell - ro) / d = q * a + o with a = cell/d, o = (p - ro)/d.  With the byte
-    // read as u = 1 + q * 2^-15:  t = u * (a * 2^15) + (o - a * 2^15)
-    const float ax = sx * r.idx * 32768.0f, ay = sy * r.idy * 32768.0f, az = sz * r.idz * 32768.0f;  // exact scalings
+    // read as u = 1 + q / kPlaneScale:  t = u * (a * kPlaneScale) + (o - a * kPlaneScale)
+    const float ax = sx * r.idx * kPlaneScale, ay = sy * r.idy * kPlaneScale, az = sz * r.idz * kPlaneScale;  // exact scalings
     const float ox = (u2f(n0.x) - r.ro.x) * r.idx - ax, oy = (u2f(n0.y) - r.ro.y) * r.idy - ay,
                 oz = (u2f(n0.z) - r.ro.z) * r.idz - az;
     // word layout: n2 = qlo.x[0..3] qlo.x[4..7] qlo.y[0..3] qlo.y[4..7]; n3 = qlo.z.. qhi.x..; n4 = qhi.y.. qhi.z..
@@ -184,17 +228,20 @@ CRT_HD uint32_t intersect_node(const Bvh& bvh, uint32_t node_idx, const RaySetup
         child_bits[w] = (meta4 >> 5) & 0x07070707u;
     }
     uint32_t hits = 0;
-#pragma unroll
-    for (int s = 0; s < 8; s++)
-    {
-        const int w = s >> 2, k = s & 3;
-        const float t0 = fmaxf(fmaxf(fmaf(byte_to_unit_float(nearx[w], k), ax, ox), fmaf(byte_to_unit_float(neary[w], k), ay, oy)),
-                               fmaxf(fmaf(byte_to_unit_float(nearz[w], k), az, oz), tmin));
-        const float t1 = fminf(fminf(fmaf(byte_to_unit_float(farx[w], k), ax, ox), fmaf(byte_to_unit_float(fary[w], k), ay, oy)),
-                               fminf(fmaf(byte_to_unit_float(farz[w], k), az, oz), tmax));
-        const uint32_t bits = ((child_bits[w] >> (8 * k)) & 0xffu) << ((bit_index[w] >> (8 * k)) & 0xffu);
-        hits |= t0 <= t1 ? bits : 0u;  // an empty slot has meta 0, hence bits 0
+    const uint32_t one = bvh.f32_one;
+#define CRT_SLOT(W, K)                                                                                                      \
+    {                                                                                                                       \
+        const float t0 = fmaxf(fmaxf(fmaf(byte_to_unit_float<K>(nearx[W], one), ax, ox),                                    \
+                                     fmaf(byte_to_unit_float<K>(neary[W], one), ay, oy)),                                   \
+                               fmaxf(fmaf(byte_to_unit_float<K>(nearz[W], one), az, oz), tmin));                            \
+        const float t1 = fminf(fminf(fmaf(byte_to_unit_float<K>(farx[W], one), ax, ox),                                     \
+                                     fmaf(byte_to_unit_float<K>(fary[W], one), ay, oy)),                                    \
+                               fminf(fmaf(byte_to_unit_float<K>(farz[W], one), az, oz), tmax));                             \
+        const uint32_t bits = ((child_bits[W] >> (8 * K)) & 0xffu) << ((bit_index[W] >> (8 * K)) & 0xffu);                  \
+        hits |= t0 <= t1 ? bits : 0u; /* an empty slot has meta 0, hence bits 0 */                                          \
     }
+    CRT_SLOT(0, 0) CRT_SLOT(0, 1) CRT_SLOT(0, 2) CRT_SLOT(0, 3) CRT_SLOT(1, 0) CRT_SLOT(1, 1) CRT_SLOT(1, 2) CRT_SLOT(1, 3)
+#undef CRT_SLOT
     child_base = n1.x;
     tri_base = n1.y;
     imask_out = imask;

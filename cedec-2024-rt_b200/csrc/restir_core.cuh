@@ -157,7 +157,12 @@ struct LightsTable
         uint32_t nth = (uint32_t)(rv0 * (float)n);
         if (nth == n) nth = n - 1;
         const char* q = (const char*)(table + nth);
+#if defined(CRT_LIGHT_LDG128)
         return Raw{load_u4(q), load_u4(q + 16), load_u4(q + 32), load_u4(q + 48)};
+#else
+        const u8w lo = load_u8w(q), hi = load_u8w(q + 32);  // two 256-bit requests per record
+        return Raw{lo.lo, lo.hi, hi.lo, hi.hi};
+#endif
     }
     CRT_HD LightSample finish(const Raw& raw, float rv1, float rv2) const
     {

@@ -254,12 +254,24 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                 bool hit = false;
                 if (valid)
                 {
-                    for (uint32_t k = g - first; k; --k) m &= m - 1u;  // drop the owner's earlier triangles
+                    // drop the owner's earlier triangles: the (g - first)-th set bit of its 24-bit mask, found by
+                    // halving (branch-free; a clear-lowest-bit loop ran up to 23 times for the warp's slowest lane)
+                    uint32_t k = g - first, shift = 0;
+#pragma unroll
+                    for (int width = 16; width; width >>= 1)
+                    {
+                        const uint32_t c = (uint32_t)__popc((m >> shift) & ((1u << width) - 1u));
+                        if (k >= c)
+                        {
+                            k -= c;
+                            shift += (uint32_t)width;
+                        }
+                    }
                     Hit h;
                     h.prim = -1;
                     h.t = 0.99f;
                     h.u = h.v = 0.0f;
-                    hit = intersect_wide_tri(bvh.tris + tri_base + (uint32_t)(__ffs((int)m) - 1), o, 0.0f, h);
+                    hit = intersect_wide_tri(bvh.tris + tri_base + shift, o, 0.0f, h);  // bit `shift` of m is that triangle
                 }
                 // lanes [excl - base, incl - base) of this round tested this lane's pairs
                 const uint32_t hits = __ballot_sync(full, hit);
