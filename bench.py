@@ -116,7 +116,7 @@ KERNEL_BYTES = {
     "raycast": (16, 16), "generate_candidate": (92, 92), "temporal_resampling": (244, 16),
     "save_temporal_reservoir": (152, 152), "spatial_resampling": (168, 16), "resolve": (124, 32), "tone_mapping": (20, 20),
     "candidate_temporal": (16 + 72 + 72 + 24 + 1, 16 + 72 + 1), "spatial_fast": (1 + 24 + 72 + 72, 1),
-    "resolve_fast": (16 + 1 + 24 + 48 + 64, 16 + 1 + 16),
+    "resolve_fast": (16 + 1 + 24 + 72 + 64, 16 + 1 + 16),
     "trace_visibility_reuse": (None, None), "trace_resolve": (None, None),  # traversal: per-ray figures below
 }
 HBM_BOUND = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampling", "tone_mapping", "spatial_fast",
@@ -175,6 +175,7 @@ def run_cuda(args):
         r.frame()
     barrier()
     launches0 = r.rt.launch_count()
+    rays0 = r.rt.shadow_rays_traced()
     sampler.mark_begin()
     # ---- timed: K frames, resident buffers
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -186,6 +187,8 @@ def run_cuda(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = r.rt.launch_count() - launches0
+    rays1 = r.rt.shadow_rays_traced()
+    shadow_rays = [(b - a) / args.steps for a, b in zip(rays0, rays1)]  # per frame: (visibility reuse, resolve)
     # ---- timed: K frames end to end (per-frame D2H of the RGBA8 image into pinned host memory)
     barrier()
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -211,15 +214,20 @@ def run_cuda(args):
     for name, t_ms in marks:
         per_kernel.setdefault(name, []).append(t_ms)
     n_px, n_diffuse = pixel_classes(torch, r)
-    rays = n_px + 2 * n_diffuse  # config 5: 1 primary per pixel + visibility-reuse + resolve ray per diffuse pixel
+    # rays actually traced per frame: 1 primary per pixel + the shadow rays counted by the tracer (the reference traces
+    # 2 per diffuse pixel; the fused frame skips those whose answer it already holds, see include/cedecrt.h)
+    rays = n_px + sum(shadow_rays)
 
-    t = torch.tensor([ms, ms_e2e, float(rays)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, ms_e2e, float(rays), float(shadow_rays[0]), float(shadow_rays[1]), float(n_px), float(n_diffuse)],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, ms_e2e, rays = tmax[0].item(), tmax[1].item(), tsum[2].item()
+    rays_vr, rays_rs, all_px, all_diffuse = (t[3].item(), t[4].item(), t[5].item(), t[6].item()) if world == 1 else \
+        (tsum[3].item(), tsum[4].item(), tsum[5].item(), tsum[6].item())
     if rank == 0:
         n_img = W * H
         peak, peak_src = measured_peaks()
@@ -233,9 +241,11 @@ def run_cuda(args):
                 k["algo_bytes_per_launch"] = int(nbytes)
                 k["algo_gbs"] = round(nbytes / per_launch / 1e6, 1)
             elif name == "trace_resolve":
-                k["algo_bytes_per_launch"] = 96 * n_diffuse  # R 64 B record, RMW float4 accumulation
-                k["algo_gbs"] = round(96 * n_diffuse / per_launch / 1e6, 1)
-                k["mrays_per_s"] = round(n_diffuse / per_launch / 1e3, 1)
+                k["algo_bytes_per_launch"] = int(96 * shadow_rays[1])  # R 64 B record, RMW float4 accumulation
+                k["algo_gbs"] = round(96 * shadow_rays[1] / per_launch / 1e6, 1)
+                k["mrays_per_s"] = round(shadow_rays[1] / per_launch / 1e3, 1)
+            elif name == "trace_visibility_reuse":
+                k["mrays_per_s"] = round(shadow_rays[0] / per_launch / 1e3, 1)
             kern[name] = k
         frame_ms_by_kernel = {k: v["ms_per_launch"] * v["launches_per_frame"] for k, v in kern.items()}
         dominant = max(frame_ms_by_kernel, key=frame_ms_by_kernel.get)
@@ -260,6 +270,12 @@ def run_cuda(args):
                        "l2": "per-frame working set (3 x 600 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
                        "math": "libdevice float (reference NVRTC semantics), -fmad=false"},
             "grays_per_s": round(rays * args.steps / ms / 1e6, 4), "rays_per_frame": int(rays),
+            "rays": {"primary": int(all_px), "visibility_reuse": int(rays_vr), "resolve": int(rays_rs),
+                     "reference_would_trace": int(all_px + 2 * all_diffuse),
+                     "note": "per frame, counted by the tracer (crt_shadow_rays_traced); the reference traces one "
+                             "visibility-reuse and one resolve ray per diffuse pixel, the fused frame omits those "
+                             "whose outcome cannot be read (candidate lost the temporal merge) or is already known "
+                             "(resolve ray identical to a traced visibility-reuse ray)"},
             "e2e": {"value": round(n_img * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s",
                     "h2d_bytes_per_step": 96, "d2h_bytes_per_step": 4 * n_img,
                     "note": "per-frame inputs (RayGenerator 36 B, eye 12 B, Options 48 B) go as kernel parameters; "

@@ -49,6 +49,7 @@ extern "C" int crt_init(int device, crt_ctx** out)
     CRT_CUDA(cudaEventCreate(&ctx->ev_stop));
     if (const char* e = getenv("CRT_WAVEFRONT")) ctx->wavefront = atoi(e);
     if (const char* e = getenv("CRT_LIGHT_TABLE")) ctx->light_table = atoi(e);
+    if (const char* e = getenv("CRT_RESOLVE_REUSE")) ctx->resolve_reuse = atoi(e);
     *out = ctx;
     return CRT_OK;
 }
@@ -98,6 +99,15 @@ extern "C" int crt_set_stream(crt_ctx* ctx, void* cuda_stream)
 }
 extern "C" void* crt_get_stream(crt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" unsigned long long crt_launch_count(crt_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+extern "C" int crt_shadow_rays_traced(crt_ctx* ctx, unsigned long long out[2])
+{
+    CRT_REQUIRE(ctx && out, "null argument");
+    out[0] = out[1] = 0;
+    if (!ctx->queue_counters) return CRT_OK;
+    CRT_CUDA(cudaMemcpyAsync(out, ctx->queue_counters + 2, 2 * sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CRT_OK;
+}
 
 extern "C" int crt_malloc(crt_ctx* ctx, size_t bytes, void** out)
 {

@@ -28,6 +28,10 @@ struct crt_ctx
     // fused frame (kernels_fast.cu): G-buffer + pixel-class plane, 25 bytes per pixel, grown on demand
     void* gbuf = nullptr;
     size_t gbuf_pixels = 0;
+    // traced marks of the temporal history (restir_fast.cuh: kTracedBit) are valid for this geometry and buffer
+    unsigned long long history_serial = 0;
+    const void* history_buffer = nullptr;
+    int resolve_reuse = 1;  // 0: resolve traces every shadow ray like the reference (CRT_RESOLVE_REUSE=0)
     // slab_p2p.cu: peer pointers of the neighbouring slabs and the exchange counter
     crt_slab_links links = {};
     bool links_set = false;
@@ -47,6 +51,7 @@ struct crt_geometry_t
     crt::WideTri* tris = nullptr;
     const crt_triangle* src = nullptr;  // the triangle array the tree was built over
     size_t n_tris = 0, n_nodes = 0;
+    unsigned long long serial = 0;  // unique per build, never 0 (crt_ctx::history_serial)
     int max_depth = 0;
     float build_ms = 0.0f;
     float pad = 0.0f;

@@ -1,6 +1,7 @@
 // geometry.cu — crt_build_geometry / crt_destroy_geometry / ray probes.
 // Replaces hiprtCreateContext + buildHiprtGeometry (10_restir_di.cpp:74-79,220; common/loader.hpp:68-112):
 // the BVH is built on the GPU from the device-resident reference Triangle array, synchronously.
+#include <atomic>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -396,6 +397,8 @@ extern "C" int crt_build_geometry(crt_ctx* ctx, const crt_triangle* d_triangles,
     CRT_REQUIRE(n < 0x7fffffffull, "too many triangles");
     CRT_CUDA(cudaSetDevice(ctx->device));
     crt_geometry_t* g = new crt_geometry_t;
+    static std::atomic<unsigned long long> next_serial{1};
+    g->serial = next_serial.fetch_add(1);
     const int rc = build(ctx, d_triangles, n, g);
     if (rc != CRT_OK)
     {

@@ -32,7 +32,11 @@ __global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
 {
     const TilePix t = this_pixel(W, H, rows);
     DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
-    if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, frame, bvh, tris60, vis, eye, lights, make_opt(options), temporal, g, peers);
+    CandPixel cp{Vis{0.0f, 0.0f, -1}, true};
+    if (t.in) cp = classify_pixel(t.px, tris60, vis);
+    // lanes 2k, 2k+1 are horizontal neighbours of the warp's 8x4 tile: they share their light-record gathers
+    const unsigned pairs = complete_pairs(__ballot_sync(0xffffffffu, t.in && !cp.skip));
+    if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, cp, frame, bvh, tris60, eye, lights, make_opt(options), temporal, g, peers, pairs);
     queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
 }
 template <int MODE>
@@ -45,17 +49,27 @@ __global__ void __launch_bounds__(256)
 }
 __global__ void __launch_bounds__(256)
     k_resolve_fast(crt_float4* accum, int W, int H, Rows rows, const float* tris60,
-                   const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q)
+                   const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q, int accumulate, int reuse_traced)
 {
     const TilePix t = this_pixel(W, H, rows);
     DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
     DeferredShade sh{{0, 0, 0}, {0, 0, 0}, 0.0f};
-    if (t.in) d = px_resolve_fast(t.px, accum, tris60, vis, res, g, sh);
+    if (t.in) d = px_resolve_fast(t.px, accum, tris60, vis, res, g, sh, accumulate != 0, reuse_traced != 0);
     ShadowRay r = to_shadow_ray(d, t.px.idx);
     r.ucw = sh.ucw;
     r.bgx = sh.bg.x; r.bgy = sh.bg.y; r.bgz = sh.bg.z;
     r.rx = sh.rad.x; r.ry = sh.rad.y; r.rz = sh.rad.z;
     queue_push(q, d.want, r);
+}
+// the traced marks of a history buffer stop being true when the geometry they were traced against is replaced
+__global__ void __launch_bounds__(256) k_clear_traced(size_t n, SoaStore s)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        uint32_t* w = s.mword((int)i);
+        const uint32_t v = *w;
+        if (v & kTracedBit) *w = v & ~kTracedBit;
+    }
 }
 // layout conversion for inspection / parity dumps / switching modes with history
 __global__ void __launch_bounds__(256) k_soa_to_aos(size_t n, SoaStore s, crt_reservoir* aos)
@@ -89,7 +103,17 @@ int ensure_gbuf(crt_ctx* ctx, size_t n, GBuf* g)
     g->cls = (uint8_t*)(g->g1 + cap * 8);
     return CRT_OK;
 }
-bool fused(const crt_options& o) { return !o.use_shadowed_target_function; }
+// The fused bodies cover every option set except rays inside the target function; M must fit the 29 bits the
+// record gives it: (M-cap + candidates) x (neighbours + 1)^passes (10_restir_di.cu:186-188, reservoir.hpp:31-37).
+bool fused(const crt_options& o)
+{
+    if (o.use_shadowed_target_function) return false;
+    double m = 21.0 * (o.ris_sample_count > 0 ? o.ris_sample_count : 0);
+    if (o.use_spatial_resampling)
+        for (int p = 0; p < o.spatial_resampling_passes && m < 1e12; p++)
+            m *= 1.0 + (o.spatial_resampling_sample_count > 0 ? o.spatial_resampling_sample_count : 0);
+    return m < (double)kMMask;
+}
 SoaStore soa(const crt_buffer& b, size_t n) { return SoaStore{(char*)b.data, n}; }
 int check_buffers(int W, int H, const crt_restir_buffers* b)
 {
@@ -185,6 +209,15 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     const crt_visibility* vis = (const crt_visibility*)b->visibility.data;
     const uint32_t n_lights = (uint32_t)bsize(lights);
     const SoaStore T = soa(b->temporal, n);
+    if (geom->serial != ctx->history_serial || b->temporal.data != ctx->history_buffer)
+    {
+        // another geometry (or another history buffer) than last frame's: its traced marks are not ours to trust
+        k_clear_traced<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, T);
+        rc = check_launch(ctx, "clear_traced");
+        if (rc != CRT_OK) return rc;
+        ctx->history_serial = geom->serial;
+        ctx->history_buffer = b->temporal.data;
+    }
     const dim3 grid = tile_grid(W, rows);
     const bool exact = ctx->math_mode == CRT_MATH_EXACT;
     const HaloPeers peers = halo_peers(ctx, 0, rows, true, n);
@@ -205,9 +238,9 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     }
     rc = check_launch(ctx, "candidate_temporal");
     if (rc != CRT_OK || !options.use_visibility_reuse) return rc;
-    ShadowSink sink{nullptr, nullptr, 0, (uint32_t*)T.plane(2, 0)};
-    if (peers.up) sink.up_plane2 = (uint32_t*)SoaStore{peers.up, n}.plane(2, 0);
-    if (peers.down) sink.down_plane2 = (uint32_t*)SoaStore{peers.down, n}.plane(2, 0);
+    ShadowSink sink{nullptr, nullptr, 0, (uint32_t*)T.plane(0, 0)};
+    if (peers.up) sink.up_plane0 = (uint32_t*)SoaStore{peers.up, n}.plane(0, 0);
+    if (peers.down) sink.down_plane0 = (uint32_t*)SoaStore{peers.down, n}.plane(0, 0);
     sink.up_first_idx = (uint32_t)((size_t)(H - peers.up_end) * W);        // rows yi < up_end
     sink.down_end_idx = (uint32_t)((size_t)(H - peers.down_begin) * W);    // rows yi >= down_begin
     return queue_trace<kEpiSoaVisibility>(ctx, geom, q, sink);
@@ -269,7 +302,8 @@ extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geo
     if (rc != CRT_OK) return rc;
     crt_float4* accum = (crt_float4*)b->accumulation.data;
     k_resolve_fast<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(accum, W, H, rows, (const float*)triangles.data,
-                                                               (const crt_visibility*)b->visibility.data, soa(fin, n), g, q);
+                                                               (const crt_visibility*)b->visibility.data, soa(fin, n), g, q,
+                                                               options.accumulate, ctx->resolve_reuse && options.use_visibility_reuse);
     rc = check_launch(ctx, "resolve_fast");
     if (rc != CRT_OK) return rc;
     rc = queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr});

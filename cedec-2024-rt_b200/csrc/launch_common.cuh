@@ -78,12 +78,17 @@ static int queue_prepare(crt_ctx* ctx, size_t n_pixels, ShadowQueue* q)
         CRT_CUDA(cudaMalloc(&ctx->queue_rays, n_pixels * sizeof(ShadowRay)));
         ctx->queue_capacity = n_pixels;
     }
-    if (!ctx->queue_counters) CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 2 * sizeof(unsigned)));
+    if (!ctx->queue_counters)
+    {
+        CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 6 * sizeof(unsigned)));  // count, next, two 64-bit totals
+        CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 6 * sizeof(unsigned), ctx->stream));
+    }
     CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 2 * sizeof(unsigned), ctx->stream));
     q->rays = (ShadowRay*)ctx->queue_rays;
     q->count = ctx->queue_counters;
     q->next = ctx->queue_counters + 1;
     q->capacity = (uint32_t)ctx->queue_capacity;
+    q->total = (unsigned long long*)(ctx->queue_counters + 2);
     return CRT_OK;
 }
 template <int EPI>

@@ -105,7 +105,7 @@ struct LightsIndexed
     {
         const float* tri;
     };
-    CRT_HD Raw fetch(float rv0) const
+    CRT_HD Raw fetch(float rv0, unsigned /*pair_mask*/ = 0u) const
     {
         uint32_t nth = (uint32_t)(rv0 * (float)n);
         if (nth == n) nth = n - 1;
@@ -151,11 +151,46 @@ struct LightsTable
     {
         u4 a, b, c, d;
     };
-    // the gather, separated from the arithmetic so that callers can have several records in flight
-    CRT_HD Raw fetch(float rv0) const
+    // the gather, separated from the arithmetic so that callers can have several records in flight.
+    //
+    // pair_mask != 0 (device only): the lanes named in it call fetch together, and with it each lane 2k and its
+    // neighbour 2k+1 are both named.  The two then share their gathers: the L1 charges one wavefront per distinct
+    // 128-byte line per load instruction, a 64-byte record needs two 256-bit loads, so a warp fetching 32 records on
+    // its own pays 64 wavefronts.  Paired, both lanes read the even lane's record in the first instruction (one
+    // half each) and the odd lane's in the second: 32 wavefronts, and the halves that landed in the partner's
+    // registers come back through eight shuffles.
+    // MEASURED AND REJECTED (profiles/r1/bench_o_pair_gather.json): k_candidate_temporal 2.19 -> 3.08 ms at 4K.  The
+    // loop issues 63 % of its cycles and the nine extra SHFL per candidate (2.26 G warp instructions against
+    // 1.76 G) cost more than the halved tag traffic saves.  Kept behind CRT_LIGHT_PAIR for the record.
+    CRT_HD Raw fetch(float rv0, unsigned pair_mask = 0u) const
     {
         uint32_t nth = (uint32_t)(rv0 * (float)n);
         if (nth == n) nth = n - 1;
+#if defined(__CUDA_ARCH__) && defined(CRT_LIGHT_PAIR) && !defined(CRT_LIGHT_LDG128)
+        const unsigned lane = threadIdx.x & 31u;
+        if ((pair_mask >> lane) & 1u)
+        {
+            const bool odd = (lane & 1u) != 0u;
+            const uint32_t other = __shfl_xor_sync(pair_mask, nth, 1);
+            const char* half = (const char*)table + (odd ? 32 : 0);
+            const u8w x = load_u8w(half + (size_t)(odd ? other : nth) * 64);  // the even lane's record
+            const u8w y = load_u8w(half + (size_t)(odd ? nth : other) * 64);  // the odd lane's record
+            // even keeps x (low half of its record) and is owed the high half = odd's x; odd keeps y (high half) and
+            // is owed the low half = even's y
+            const u8w send = odd ? x : y;
+            u8w recv;
+            recv.lo.x = __shfl_xor_sync(pair_mask, send.lo.x, 1);
+            recv.lo.y = __shfl_xor_sync(pair_mask, send.lo.y, 1);
+            recv.lo.z = __shfl_xor_sync(pair_mask, send.lo.z, 1);
+            recv.lo.w = __shfl_xor_sync(pair_mask, send.lo.w, 1);
+            recv.hi.x = __shfl_xor_sync(pair_mask, send.hi.x, 1);
+            recv.hi.y = __shfl_xor_sync(pair_mask, send.hi.y, 1);
+            recv.hi.z = __shfl_xor_sync(pair_mask, send.hi.z, 1);
+            recv.hi.w = __shfl_xor_sync(pair_mask, send.hi.w, 1);
+            const u8w lo = odd ? recv : x, hi = odd ? y : recv;
+            return Raw{lo.lo, lo.hi, hi.lo, hi.hi};
+        }
+#endif
         const char* q = (const char*)(table + nth);
 #if defined(CRT_LIGHT_LDG128)
         return Raw{load_u4(q), load_u4(q + 16), load_u4(q + 32), load_u4(q + 48)};
@@ -190,7 +225,7 @@ CRT_HD float geometry_term(f3 p0, f3 n0, f3 p1, f3 n1)  // core.hpp:287-295
 struct Sample
 {
     f3 op, on, hp, hn, rad;  // origin position/normal, hit position/normal, radiance
-    uint32_t vis;            // bool visibility
+    uint32_t vis;            // bit 0: bool visibility; bit 1 (fused frame only): traced, see restir_fast.cuh kSampleTraced
 };
 struct Res
 {
@@ -285,8 +320,10 @@ CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, 
 #define CRT_RIS_BATCH 2
 #endif
 constexpr int kRisBatch = CRT_RIS_BATCH;
+// pair_mask: see LightsTable::fetch; every lane named in it must run this loop with the same `count`
 template <class L>
-CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int count, bool shadowed, Pcg& rng)
+CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int count, bool shadowed, Pcg& rng,
+                          unsigned pair_mask = 0u)
 {
     Res r = empty_res();
     const float inv_n = 1.0f / (float)lights.n;
@@ -302,7 +339,7 @@ CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int
             r1[b] = rng.next_f();
             r2[b] = rng.next_f();
             u[b] = rng.next_f();
-            raw[b] = lights.fetch(r0);
+            raw[b] = lights.fetch(r0, pair_mask);
         }
 #pragma unroll
         for (int b = 0; b < kRisBatch; ++b) ris_update(bvh, surf, lights.finish(raw[b], r1[b], r2[b]), inv_n, u[b], shadowed, r);
@@ -313,7 +350,7 @@ CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int
         const float r1 = rng.next_f();
         const float r2 = rng.next_f();
         const float u = rng.next_f();
-        ris_update(bvh, surf, lights.sample(r0, r1, r2), inv_n, u, shadowed, r);
+        ris_update(bvh, surf, lights.finish(lights.fetch(r0, pair_mask), r1, r2), inv_n, u, shadowed, r);
     }
     return r;
 }
@@ -325,7 +362,7 @@ CRT_HD bool temporal_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& 
     const int cap = 20 * opt.ris_count;  // M-cap, :186-188
     prev.M = prev.M < cap ? prev.M : cap;
     float p_hat_y = target_function(bvh, surf.p, surf.n, prev.s.hp, prev.s.hn, prev.s.rad, opt.shadowed);
-    if (opt.reuse) p_hat_y *= prev.s.vis ? 1.0f : 0.0f;
+    if (opt.reuse) p_hat_y *= (prev.s.vis & 1u) ? 1.0f : 0.0f;
     prev.M = f2i_trunc((float)prev.M * rejection_heuristics<M>(r.s, prev.s, eye));  // int *= float, :211-212
     const float weight = p_hat_y * prev.ucw * (float)prev.M;
     const float u = rng.next_f();
@@ -337,12 +374,18 @@ CRT_HD bool temporal_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& 
     return accepted;  // false: the sample of `r` (this frame's candidate) survived
 }
 
+// M of a merged reservoir after the probabilistic rejection (reservoir.hpp:61-87; int *= float, 10_restir_di.cu:211-212, 357-358)
+template <class M>
+CRT_HD int rejected_m(const Sample& mine, const Sample& theirs, int their_m, f3 eye)
+{
+    return f2i_trunc((float)their_m * rejection_heuristics<M>(mine, theirs, eye));
+}
 // one neighbour of spatial_resampling (10_restir_di.cu:340-370); compares against the *running* reservoir
 template <class M>
 CRT_HD void spatial_merge(const Bvh& bvh, const Surf& surf, f3 eye, const Opt& opt, Res nb, Res& r, Pcg& rng)
 {
     float p_hat_y = target_function(bvh, surf.p, surf.n, nb.s.hp, nb.s.hn, nb.s.rad, opt.shadowed);
-    if (opt.reuse) p_hat_y *= nb.s.vis ? 1.0f : 0.0f;
+    if (opt.reuse) p_hat_y *= (nb.s.vis & 1u) ? 1.0f : 0.0f;
     nb.M = f2i_trunc((float)nb.M * rejection_heuristics<M>(r.s, nb.s, eye));
     const float weight = p_hat_y * nb.ucw * (float)nb.M;
     const float u = rng.next_f();  // third random only for neighbours that survive the rejections

@@ -52,7 +52,7 @@ struct AosStore
         r.s.hp = {p[6], p[7], p[8]};
         r.s.hn = {p[9], p[10], p[11]};
         r.s.rad = {p[12], p[13], p[14]};
-        r.s.vis = f2u(p[15]) & 0xffu;
+        r.s.vis = (f2u(p[15]) & 0xffu) ? 1u : 0u;
         r.w_sum = p[16];
         r.ucw = p[17];
         r.M = (int)f2u(p[18]);
@@ -66,7 +66,7 @@ struct AosStore
         p[6] = r.s.hp.x; p[7] = r.s.hp.y; p[8] = r.s.hp.z;
         p[9] = r.s.hn.x; p[10] = r.s.hn.y; p[11] = r.s.hn.z;
         p[12] = r.s.rad.x; p[13] = r.s.rad.y; p[14] = r.s.rad.z;
-        p[15] = u2f(r.s.vis ? 1u : 0u);
+        p[15] = u2f(r.s.vis & 1u);
         p[16] = r.w_sum;
         p[17] = r.ucw;
         p[18] = u2f((uint32_t)r.M);

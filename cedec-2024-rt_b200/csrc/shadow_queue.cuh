@@ -34,6 +34,7 @@ struct ShadowQueue
     uint32_t* count;   // rays appended so far
     uint32_t* next;    // next ray to fetch (persistent kernel)
     uint32_t capacity;
+    unsigned long long* total;  // rays traced since crt_init: [0] visibility reuse, [1] resolve (crt_shadow_rays_traced)
 };
 
 #ifndef CRT_REFILL
@@ -67,7 +68,7 @@ enum
 {
     kEpiReservoirVisibility = 0,  // reservoirs[pix].sample.visibility = !occluded   (generate_candidate, AoS)
     kEpiResolve = 1,              // accumulation[pix] (+)= brdf*G*V*radiance*ucw     (resolve)
-    kEpiSoaVisibility = 2         // fused frame: set the visibility bit of the SoA reservoir (restir_fast.cuh)
+    kEpiSoaVisibility = 2         // fused frame: set the visibility bit of the reservoir record (restir_fast.cuh)
 };
 
 struct ShadowSink
@@ -75,11 +76,11 @@ struct ShadowSink
     crt_reservoir* reservoirs;  // kEpiReservoirVisibility
     crt_float4* accumulation;   // kEpiResolve*
     int accumulate;
-    uint32_t* soa_plane2;       // kEpiSoaVisibility: plane 2 of the SoA reservoir buffer (M | visibility << 31 in word 2)
-    // multi-GPU slabs: plane 2 of the neighbours' copies; pixel indices below up_end_idx belong... see HaloPeers.
+    uint32_t* soa_plane0;       // kEpiSoaVisibility: plane 0 of the reservoir storage (flags | M in word kMWord of 8)
+    // multi-GPU slabs: plane 0 of the neighbours' copies; pixel indices below up_end_idx belong... see HaloPeers.
     // Bottom-up storage: rows yi < up_end are the pixel indices >= up_first_idx, rows yi >= down_begin those < down_end_idx
-    uint32_t* up_plane2 = nullptr;
-    uint32_t* down_plane2 = nullptr;
+    uint32_t* up_plane0 = nullptr;
+    uint32_t* down_plane0 = nullptr;
     uint32_t up_first_idx = 0, down_end_idx = 0;
 };
 
@@ -98,10 +99,11 @@ __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const Sh
         // the reservoir was stored with visibility = false; only this thread touches the word now
         if (!occluded)
         {
-            const uint32_t w = sink.soa_plane2[(size_t)pix * 4 + 2] | kVisBit;
-            sink.soa_plane2[(size_t)pix * 4 + 2] = w;
-            if (sink.up_plane2 && pix >= sink.up_first_idx) sink.up_plane2[(size_t)pix * 4 + 2] = w;
-            if (sink.down_plane2 && pix < sink.down_end_idx) sink.down_plane2[(size_t)pix * 4 + 2] = w;
+            const size_t at = (size_t)pix * 8 + kMWord;
+            const uint32_t w = sink.soa_plane0[at] | kVisBit;
+            sink.soa_plane0[at] = w;
+            if (sink.up_plane0 && pix >= sink.up_first_idx) sink.up_plane0[at] = w;
+            if (sink.down_plane0 && pix < sink.down_end_idx) sink.down_plane0[at] = w;
         }
     }
     else
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
     const uint32_t n_rays = *q.count;
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.total + (EPI == kEpiResolve ? 1 : 0), (unsigned long long)n_rays);
 
     bool active = false, exhausted = false;
     RaySetup r;

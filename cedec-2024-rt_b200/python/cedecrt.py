@@ -179,6 +179,8 @@ def _load():
     lib.crt_device_name.argtypes = [P]
     lib.crt_get_stream.restype = C.c_void_p
     lib.crt_get_stream.argtypes = [P]
+    lib.crt_shadow_rays_traced.restype = C.c_int
+    lib.crt_shadow_rays_traced.argtypes = [P, C.POINTER(C.c_ulonglong)]
     lib.crt_launch_count.restype = C.c_ulonglong
     lib.crt_launch_count.argtypes = [P]
     lib.crt_raygen_lookat.restype = None
@@ -316,6 +318,12 @@ class Runtime:
 
     def launch_count(self):
         return int(self.lib.crt_launch_count(self.ctx))
+
+    def shadow_rays_traced(self):
+        """(visibility-reuse rays, resolve rays) traced through the wavefront queue since crt_init (synchronises)"""
+        out = (C.c_ulonglong * 2)()
+        self._check(self.lib.crt_shadow_rays_traced(self.ctx, out))
+        return int(out[0]), int(out[1])
 
     def sync(self):
         self._check(self.lib.crt_sync(self.ctx))

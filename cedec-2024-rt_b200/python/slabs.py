@@ -81,8 +81,8 @@ def halo_plan(H, edges, rank, halo=HALO):
 def row_byte_ranges(W, H, rows, layout):
     """byte ranges [(begin, end)] that image rows [a, b) occupy in a bottom-up buffer.
     layout: ("aos", elem_bytes) — one contiguous range; ("planes", [elem_bytes...]) — planar storage over W*H
-    pixels, planes back to back in the order given, each plane padded to 16 * W * H bytes except the last ones
-    as in csrc/restir_fast.cuh (plane p starts at sum of 16*W*H for the planes before it)."""
+    pixels, planes back to back in the order given (plane p starts where plane p-1 ends), as in
+    csrc/restir_fast.cuh: soa_plane_offset."""
     a, b = rows
     first, last = (H - b) * W, (H - a) * W
     if layout[0] == "aos":
@@ -91,11 +91,11 @@ def row_byte_ranges(W, H, rows, layout):
     out, off = [], 0
     for e in layout[1]:
         out.append((off + first * e, off + last * e))
-        off += 16 * W * H if e == 16 else e * W * H
+        off += e * W * H
     return out
 
 
-SOA_RESERVOIR = ("planes", [16, 16, 16, 16, 8])  # csrc/restir_fast.cuh: SoaStore
+SOA_RESERVOIR = ("planes", [32, 32, 8])  # csrc/restir_fast.cuh: SoaStore
 AOS_RESERVOIR = ("aos", 76)
 AOS_VISIBILITY = ("aos", 16)
 CLASS_PLANE = ("aos", 1)

@@ -93,6 +93,10 @@ int crt_set_stream(crt_ctx* ctx, void* cuda_stream);
 void* crt_get_stream(crt_ctx* ctx);
 /* number of CUDA kernels this context has launched so far (bench.py reports it as gpu_launches) */
 unsigned long long crt_launch_count(crt_ctx* ctx);
+/* shadow rays (check_visibility, raytrace.hpp:45-52) traced through the wavefront queue since crt_init — out[0]
+ * visibility-reuse rays (10_restir_di.cu:127-131), out[1] resolve rays (:443-444); waits for the stream.  The fused frame traces fewer than the reference's two per diffuse pixel: the visibility-reuse ray
+ * only for candidates that survive the temporal merge, the resolve ray only when it has not been traced before. */
+int crt_shadow_rays_traced(crt_ctx* ctx, unsigned long long out[2]);
 /* TypedBuffer<T>(DEVICE).allocate / dtor / toDevice / toHost (common/typedbuffer.hpp:29-77);
  * memory is uninitialised, as with oroMalloc */
 int crt_malloc(crt_ctx* ctx, size_t bytes, void** out);
@@ -179,14 +183,17 @@ int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int width, int
 /* ---- fused frame ("fast mode").  One call replaces the launch list of a frame
  * (examples/10_restir_di/10_restir_di.cpp:270-372: raycast ... tone_mapping) with identical results in
  * `accumulation`, `pixels` and `visibility`.  The three TypedBuffer<Reservoir> allocations (W*H*76 bytes each, as
- * the reference allocates them, :112-122) are used as OPAQUE storage: inside, reservoirs are planar SoA
- *   plane p (p = 0..3) at byte offset p*16*W*H, 16 bytes per pixel; plane 4 at 64*W*H, 8 bytes per pixel
- *   (field order: csrc/restir_fast.cuh), pixel order = the reference's pixel_idx (bottom-up rows),
+ * the reference allocates them, :112-122) are used as OPAQUE storage: inside, reservoirs are sector-planar
+ *   plane 0 at byte offset 0 and plane 1 at 32*W*H, 32 bytes per pixel; plane 2 at 64*W*H, 8 bytes per pixel
+ *   (field order and flag bits: csrc/restir_fast.cuh), pixel order = the reference's pixel_idx (bottom-up rows),
  * candidate generation and temporal resampling are one kernel that rewrites `temporal` in place (no
  * save_temporal_reservoir), spatial pass 0 reads `temporal` and writes reservoir1, later passes ping-pong
  * reservoir1 <-> reservoir0, and tone mapping is part of resolve.  crt_reservoir_export_aos converts a buffer to
- * the reference's AoS for inspection.  With use_shadowed_target_function the same calls run the per-kernel path on
- * AoS buffers instead (crt_restir_is_fused tells which); do not mix the two on one set of buffers. */
+ * the reference's AoS for inspection.  With use_shadowed_target_function (or option values that would let M pass
+ * 2^29) the same calls run the per-kernel path on AoS buffers instead (crt_restir_is_fused tells which); do not mix
+ * the two on one set of buffers.  resolve does not re-trace a shadow ray whose answer the history already holds
+ * (same origin, same target, same geometry: csrc/restir_fast.cuh kTracedBit); CRT_RESOLVE_REUSE=0 in the
+ * environment of crt_init makes it trace every ray like the reference.  Images are bit-identical either way. */
 typedef struct
 {
     crt_buffer pixels;        /* TypedBuffer<uint8_t>   4*W*H   (10_restir_di.cpp:96-97)  */

@@ -61,6 +61,8 @@ struct EmuGeom
     Bvh view() const { return Bvh{nodes.data(), tris.data(), kPostponeRatio}; }
 };
 int g_math_mode = 0;
+int g_resolve_reuse = 1;
+long g_resolve_rays = 0;
 long g_tid_begin = 0, g_tid_end = -1;
 
 // same sequence as csrc/geometry.cu:build(), one loop per kernel
@@ -329,7 +331,7 @@ extern "C"
     }
 
     // ---- the fused frame (csrc/kernels_fast.cu: crt_restir_di_frame), same kernel sequence, rays traced inline.
-    // temporal / res_a / res_b: planar SoA storage of W*H*76 bytes each (restir_fast.cuh: SoaStore).
+    // temporal / res_a / res_b: sector-planar storage of W*H*76 bytes each (restir_fast.cuh: SoaStore).
     // Final spatial output: res_a for an odd number of passes, res_b for an even one, `temporal` if spatial is off.
     void emu_restir_frame_fast(int W, int H, int frame, void* gp, const crt_triangle* tris, const crt_raygen* rg,
                                const float* eye_p, const uint32_t* lights, int nlights, const crt_options* options,
@@ -349,12 +351,13 @@ extern "C"
         launch(W, H, [&](Pix p) { px_raycast(p, W, H, bvh, *rg, vis); });
         launch(W, H, [&](Pix p)
                {
-                   const DeferredRay d = g_math_mode ? px_candidate_temporal<Math<1>>(p, frame, bvh, t60, vis, eye, L, opt, T, g)
-                                                     : px_candidate_temporal<Math<0>>(p, frame, bvh, t60, vis, eye, L, opt, T, g);
+                   const CandPixel cp = classify_pixel(p, t60, vis);
+                   const DeferredRay d = g_math_mode ? px_candidate_temporal<Math<1>>(p, cp, frame, bvh, t60, eye, L, opt, T, g)
+                                                     : px_candidate_temporal<Math<0>>(p, cp, frame, bvh, t60, eye, L, opt, T, g);
                    if (d.want)
                    {
                        Hit h;
-                       if (!trace<true>(bvh, d.org, d.dir, 0.0f, 0.99f, h)) *T.mvis_word(p.idx) |= kVisBit;
+                       if (!trace<true>(bvh, d.org, d.dir, 0.0f, 0.99f, h)) *T.mword(p.idx) |= kVisBit;
                    }
                });
         SoaStore in = T, out = A;
@@ -373,13 +376,24 @@ extern "C"
         launch(W, H, [&](Pix p)
                {
                    DeferredShade sh{{0, 0, 0}, {0, 0, 0}, 0.0f};
-                   const DeferredRay d = px_resolve_fast(p, accum, t60, vis, fin, g, sh);
+                   const DeferredRay d = px_resolve_fast(p, accum, t60, vis, fin, g, sh, opt.accumulate, g_resolve_reuse && opt.reuse);
                    if (!d.want) return;
+#pragma omp atomic
+                   g_resolve_rays++;
                    Hit h;
                    const float V = trace<true>(bvh, d.org, d.dir, 0.0f, 0.99f, h) ? 0.0f : 1.0f;
                    write_accum(accum, p.idx, sh.bg * V * sh.rad * sh.ucw, opt.accumulate);  // shadow_epilogue<kEpiResolve>
                });
         orc_tone_mapping(pixels, accum, W, H);
+    }
+    // resolve: 1 (default) uses the stored answer of an already traced shadow ray, 0 traces every ray (kernels_fast.cu:
+    // crt_ctx::resolve_reuse); emu_resolve_rays: shadow rays traced by resolve since the last call
+    void emu_set_resolve_reuse(int v) { g_resolve_reuse = v; }
+    long emu_resolve_rays()
+    {
+        const long r = g_resolve_rays;
+        g_resolve_rays = 0;
+        return r;
     }
     void emu_soa_to_aos(const char* soa, crt_reservoir* aos, long n)
     {

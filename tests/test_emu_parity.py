@@ -253,6 +253,38 @@ def test_fused_frame_equals_kernel_chain(emu, port, variant, mode):
         emu.set_math_mode(0)
 
 
+def test_resolve_reuses_traced_visibility(emu, port):
+    """resolve's shadow ray towards a sample whose origin is this pixel's own surface is the visibility-reuse ray
+    already traced for that sample: using the stored answer (restir_fast.cuh: kTracedBit) changes no bit of the
+    image and saves rays"""
+    tris = lit_blocks_ao()
+    W, H = 96, 54
+    opt = orc.make_options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    g = port.geom_build(tris)
+    ch = orc.RestirChain(port, W, H, tris, g, *CAM_AO, opt)
+    ge = emu.geom_build(tris)
+    emu.lib.emu_resolve_rays.restype = C.c_long
+    rays = {}
+    try:
+        for reuse in (1, 0):
+            emu.lib.emu_set_resolve_reuse(reuse)
+            fu = EmuFusedFrame(emu, W, H, tris, ge, *CAM_AO, opt)
+            emu.lib.emu_resolve_rays()
+            for f in range(4):
+                fu.step()
+                if reuse:
+                    ch.step()
+                    assert same(ch.accum, fu.accum), f
+            rays[reuse] = emu.lib.emu_resolve_rays()
+            assert same(ch.accum, fu.accum)
+    finally:
+        emu.lib.emu_set_resolve_reuse(1)
+    d = int(diffuse_mask(ch.vis, tris).sum())
+    assert rays[0] == 4 * d and 0 < rays[1] < 0.95 * rays[0], (rays, d)
+    port.geom_free(g)
+    emu.geom_free(ge)
+
+
 def test_soa_aos_round_trip(emu):
     rng = np.random.default_rng(5)
     n = 1000
@@ -261,7 +293,7 @@ def test_soa_aos_round_trip(emu):
         a[f] = rng.standard_normal((n, 3)).astype(np.float32)
     a["visibility"] = rng.integers(0, 2, n)
     a["w_sum"], a["ucw"] = rng.random(n, np.float32), rng.random(n, np.float32)
-    a["M"] = rng.integers(0, 2**31 - 1, n)
+    a["M"] = rng.integers(0, 2**29 - 1, n)  # 29 bits of M in the record, 3 flag bits (restir_fast.cuh)
     soa = np.zeros(n * 76, np.uint8)
     emu.lib.emu_aos_to_soa(a.ctypes.data_as(C.c_void_p), soa.ctypes.data_as(C.c_void_p), C.c_long(n))
     b = np.zeros(n, orc.RESERVOIR)

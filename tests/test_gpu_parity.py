@@ -418,6 +418,37 @@ def test_fused_equals_per_kernel_path_default_math(rt, scene):
     assert float(a.accumulation.to_host().view(np.float32).reshape(-1, 4)[:, :3].sum()) > 0
 
 
+def test_resolve_reuse_of_traced_visibility_changes_no_bit(rt):
+    """resolve skips the shadow rays whose answer the reservoir already carries (restir_fast.cuh: kTracedBit); a
+    context created with CRT_RESOLVE_REUSE=0 traces every resolve ray like the reference.  Same images, fewer rays."""
+    tris = staged("blocks_restir")
+    W, H, frames = 960, 540, 4
+    kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    os.environ["CRT_RESOLVE_REUSE"] = "0"
+    try:
+        rt0 = cedecrt.Runtime(0)
+    finally:
+        del os.environ["CRT_RESOLVE_REUSE"]
+    try:
+        out = []
+        for r in (rt, rt0):
+            app = cedecrt.RestirDI(r, W, H, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
+            before = r.shadow_rays_traced()
+            for _ in range(frames):
+                app.frame()
+            after = r.shadow_rays_traced()
+            out.append((app.accumulation.to_host(), app.pixels.to_host(), app.export_aos(app.temporal),
+                        after[0] - before[0], after[1] - before[1], app.visibility.to_host()))
+        a, b = out
+        assert same(a[0], b[0]) and same(a[1], b[1]) and reservoir_mismatch(a[2], b[2]) == 0
+        n_diffuse = int(diffuse_mask(a[5], tris).sum())
+        assert b[4] == frames * n_diffuse           # the reference's count: one resolve ray per diffuse pixel
+        assert a[3] == b[3] and 0 < a[3] <= frames * n_diffuse
+        assert 0.3 * b[4] < a[4] < 0.95 * b[4], (a[4], b[4])
+    finally:
+        rt0.close()
+
+
 def test_reservoir_layout_round_trip(rt):
     n_w, n_h = 64, 16
     n = n_w * n_h
@@ -427,7 +458,7 @@ def test_reservoir_layout_round_trip(rt):
         a[f] = rng.standard_normal((n, 3)).astype(np.float32)
     a["visibility"] = rng.integers(0, 2, n)
     a["w_sum"], a["ucw"] = rng.random(n, np.float32), rng.random(n, np.float32)
-    a["M"] = rng.integers(0, 2**31 - 1, n)
+    a["M"] = rng.integers(0, 2**29 - 1, n)  # 29 bits of M in the record (restir_fast.cuh)
     d_a, d_s, d_b = rt.to_device(a), rt.buffer(cedecrt.RESERVOIR, n), rt.buffer(cedecrt.RESERVOIR, n)
     rt.reservoir_import_aos(n_w, n_h, d_a, d_s)
     rt.reservoir_export_aos(n_w, n_h, d_s, d_b)
