@@ -133,7 +133,10 @@ struct BinTree
 CRT_HD uint32_t bin_tri_count(const BinTree& bt, uint32_t id) { return id >= bt.n - 1 ? 1u : bt.count[id]; }
 
 // SAH constants: one node step (8 child boxes) vs one triangle test, as in Ylitie et al. 2017
-constexpr float kCostNode = 1.0f, kCostTri = 0.3f, kCostInf = 1.0e30f;
+#ifndef CRT_COST_TRI
+#define CRT_COST_TRI 0.3f
+#endif
+constexpr float kCostNode = 1.0f, kCostTri = CRT_COST_TRI, kCostInf = 1.0e30f;
 
 // c(n,1) = min(leaf, internal);  internal = distribute(n,8) + area * kCostNode
 // c(n,i) = min(distribute(n,i), c(n,i-1)), i = 2..7;  distribute(n,j) = min_k c(left,k) + c(right,j-k)

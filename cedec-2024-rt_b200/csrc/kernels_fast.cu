@@ -39,8 +39,11 @@ __global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
     if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, cp, frame, bvh, tris60, eye, lights, make_opt(options), temporal, g, peers, pairs);
     queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
 }
+#ifndef CRT_SP_MINBLOCKS
+#define CRT_SP_MINBLOCKS 4  // 64 registers: 0.83 -> 0.75 ms per pass against 3 (profiles/r1/tuning_q.txt)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CRT_SP_MINBLOCKS)
     k_spatial_fast(int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye, crt_options options, SoaStore in,
                    SoaStore out, GBuf g, HaloPeers peers)
 {
