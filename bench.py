@@ -43,6 +43,31 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1", "ncu_q_summary.csv")  # committed `ncu --set full` capture, N = 1, 4K
+NCU_NAMES = {"raycast": "k_raycast", "candidate_temporal": "k_candidate_temporal", "spatial_fast": "k_spatial_fast",
+             "resolve_fast": "k_resolve_fast", "tone_mapping": "k_tone_mapping",
+             "trace_visibility_reuse": "k_trace_shadow_queue<2>", "trace_resolve": "k_trace_shadow_queue<1>"}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed capture (bytes), or None"""
+    import csv
+
+    key = NCU_NAMES.get(kernel)
+    if not key or not os.path.exists(NCU_SUMMARY):
+        return None
+    rows = list(csv.reader(open(NCU_SUMMARY)))
+    h = rows[0]
+    try:
+        ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    vals = [float(r[ir]) * scale.get(rows[1][ir], 1.0) + float(r[iw]) * scale.get(rows[1][iw], 1.0)
+            for r in rows[2:] if key in r[0]]
+    return int(sum(vals) / len(vals)) if vals else None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
@@ -153,6 +178,11 @@ def run_cuda(args):
     # default stream's handle is 0, which crt_set_stream reads as "use the context's own stream".)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    # stdout carries exactly one JSON line: whatever libraries print while the run lasts (the image sets
+    # NCCL_DEBUG=VERSION, so NCCL writes a version banner to file descriptor 1) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tris, cam, workload = load_workload()
@@ -190,18 +220,45 @@ def run_cuda(args):
     rays1 = r.rt.shadow_rays_traced()
     shadow_rays = [(b - a) / args.steps for a, b in zip(rays0, rays1)]  # per frame: (visibility reuse, resolve)
     # ---- timed: K frames end to end (per-frame D2H of the RGBA8 image into pinned host memory)
+    if args.readback == "pipelined":
+        r.wait_download(r.download_pixels_async())  # allocates the copy stream and the pinned images, untimed
     barrier()
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_e0.record()
-    for _ in range(args.steps):
-        r.frame()
-        r.download_pixels()
-        torch.cuda.current_stream().synchronize()  # oroStreamSynchronize after the copy (10_restir_di.cpp:389)
+    if args.readback == "sync":
+        for _ in range(args.steps):
+            r.frame()
+            r.download_pixels()
+            torch.cuda.current_stream().synchronize()  # oroStreamSynchronize after the copy (10_restir_di.cpp:389)
+    else:
+        # pipelined: frame i's image travels on a copy stream while frame i+1 renders; the host takes delivery of
+        # image i-1 (one frame of latency, as a display loop has); every frame's copy lies inside the timed region
+        prev = None
+        for _ in range(args.steps):
+            r.frame()
+            slot = r.download_pixels_async()
+            if prev is not None:
+                r.wait_download(prev)
+            prev = slot
+        r.wait_download(prev)
+        torch.cuda.current_stream().wait_event(r._copy_events[prev])
     t_e1.record()
     barrier()
     ms_e2e = t_e0.elapsed_time(t_e1)
+    # ---- the two timed regions together can be shorter than nvidia-smi's sampling period (8 frames at N = 8 take
+    # 16 ms): keep the same frames running, untimed, until the sampled window under load is about 1.5 s long
+    n_probe = torch.tensor([max(0, int((1.5 - (time.time() - sampler.t0)) / max(ms / args.steps / 1e3, 1e-4)))],
+                           dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(n_probe, 0)
+    for _ in range(min(int(n_probe.item()), 5000)):
+        r.frame()
+    barrier()
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "%s + %d more frames of the same loop (untimed), %.2f s under load" % (
+            clocks.get("window", "timed regions"), int(n_probe.item()), sampler.t1 - sampler.t0)
     # ---- per-kernel device times: an event after every launch (crt_profile_begin/end), steady-state frames
     n_prof = max(2, min(args.steps, 4))
     r.halo_bytes = 0
@@ -278,13 +335,19 @@ def run_cuda(args):
                              "(resolve ray identical to a traced visibility-reuse ray)"},
             "e2e": {"value": round(n_img * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s",
                     "h2d_bytes_per_step": 96, "d2h_bytes_per_step": 4 * n_img,
+                    "readback": args.readback,
                     "note": "per-frame inputs (RayGenerator 36 B, eye 12 B, Options 48 B) go as kernel parameters; "
-                            "the RGBA8 frame is copied to pinned host memory every step"},
+                            "the RGBA8 frame is copied to pinned host memory every step" + (
+                                " on a copy stream, overlapped with the next frame (SlabRenderer.download_pixels_async)"
+                                if args.readback == "pipelined" else
+                                " on the frame's stream, followed by a stream synchronise (10_restir_di.cpp:386-389)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dominant, "bound": "hbm",
                          "achieved": dom.get("algo_gbs"), "peak": peak, "unit": "GB/s",
-                         "frac": round(dom["algo_gbs"] / peak, 4) if dom.get("algo_gbs") else None, "traffic": None,
+                         "frac": round(dom["algo_gbs"] / peak, 4) if dom.get("algo_gbs") else None,
+                         "traffic": ncu_traffic(dominant) if (world == 1 and fused and (W, H) == (W4K, H4K)) else None,
+                         "traffic_source": "profiles/r1/ncu_q_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                          "peak_source": peak_src,
                          "note": "dominant kernel by time. Traversal kernels (raycast, trace_*) are SM-issue-bound, not "
                                  "HBM-bound: see profiles/ for issue utilisation and L1/L2 hit rates; the HBM-bound "
@@ -298,7 +361,8 @@ def run_cuda(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(r, tris, cam, W, H)
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -423,6 +487,9 @@ def main():
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal-height slabs (no calibration frames)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1, fused mode: halo rows by direct peer stores (default) or NCCL send/recv")
+    ap.add_argument("--readback", default="pipelined", choices=["pipelined", "sync"],
+                    help="e2e: overlap each frame's device->host copy with the next frame (default) or copy and "
+                         "synchronise after every frame like the reference's loop")
     ap.add_argument("--mode", default="fused", choices=["fused", "dropin"],
                     help="fused: one crt_restir_* frame call sequence (default); dropin: the reference's launch list")
     args = ap.parse_args()

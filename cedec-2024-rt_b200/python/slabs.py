@@ -184,6 +184,12 @@ class SlabRenderer:
         self.frame_index = 0
         self.t_cls = None
         self.halo_bytes = 0
+        # pipelined read-back (download_pixels_async): copy stream, two pinned host images, the last copy's event
+        self._copy_stream = None
+        self._copy_events = [None, None]
+        self._host_ring = None
+        self._copies = 0
+        self._copy_pending = None
         if self.p2p:
             self._connect_peers()
 
@@ -269,6 +275,7 @@ class SlabRenderer:
             for k in range(o.spatial_resampling_passes):  # input of pass k: temporal, reservoir1, reservoir0, ...
                 rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), self.bufs)  # rows were mirrored by the kernels
                 rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
+            self._before_pixels_rewrite()
             rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
             return
         if self.fused:
@@ -280,6 +287,7 @@ class SlabRenderer:
             for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
                 self.exchange(self.t_tmp if k == 0 else (self.t_r1 if k % 2 else self.t_r0), SOA_RESERVOIR)
                 rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
+            self._before_pixels_rewrite()
             rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
             return
         rt.raycast(W, H, g, t, self.raygen, v)
@@ -295,8 +303,44 @@ class SlabRenderer:
             self.exchange(ti, AOS_RESERVOIR)
             rt.spatial_resampling(W, H, f, k, g, t, v, eye, o, bi, bo)
         rt.resolve(self.accumulation, W, H, g, t, v, eye, o, bo)
+        self._before_pixels_rewrite()
         rt.tone_mapping(self.pixels, self.accumulation, W, H)
 
     def download_pixels(self):
+        """the reference's read-back (10_restir_di.cpp:386-389): copy on the frame's own stream; the caller synchronises"""
         src = self._rows(self.t_pix, 4, self.y0, self.y1)
         self.host_pixels.copy_(src, non_blocking=True)
+
+    def download_pixels_async(self):
+        """Pipelined read-back: this frame's RGBA8 rows travel to pinned host memory on a copy stream while the next
+        frame renders; the next frame's tone mapping (the only writer of the pixel buffer) waits for the copy.  Returns
+        the index of the host image (0/1) the rows land in; wait_download(i) blocks until they are there."""
+        torch = self.torch
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        n = 4 * self.W * max(self.y1 - self.y0, 1)
+        if self._host_ring is None or self._host_ring[0].numel() != n:
+            self._host_ring = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        slot = self._copies % 2
+        self._copies += 1
+        rendered = torch.cuda.Event()
+        rendered.record()  # on the frame's stream
+        self._copy_stream.wait_event(rendered)
+        src = self._rows(self.t_pix, 4, self.y0, self.y1)
+        with torch.cuda.stream(self._copy_stream):
+            self._host_ring[slot].copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        self._copy_events[slot] = done
+        self._copy_pending = done
+        return slot
+
+    def wait_download(self, slot):
+        if self._copy_events[slot] is not None:
+            self._copy_events[slot].synchronize()
+        return self._host_ring[slot]
+
+    def _before_pixels_rewrite(self):
+        if self._copy_pending is not None:
+            self.torch.cuda.current_stream().wait_event(self._copy_pending)
+            self._copy_pending = None
