@@ -191,7 +191,7 @@ def run_cuda(args):
     r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
     stats = r.geom.stats()
     if world > 1 and not args.no_balance:
-        r.calibrate()  # static camera: balance the slab heights on throw-away frames before the sequence starts
+        r.calibrate(rounds=3, frames=4)  # static camera: balance the slab heights on throw-away frames before the sequence starts
 
     def barrier():
         if world > 1:
@@ -275,6 +275,11 @@ def run_cuda(args):
     # 2 per diffuse pixel; the fused frame skips those whose answer it already holds, see include/cedecrt.h)
     rays = n_px + sum(shadow_rays)
 
+    own_ms = sum(t_ms for name, t_ms in marks if name != "signal_wait") / n_prof  # this slab's kernels, waiting excluded
+    slab_ms = torch.zeros(world, dtype=torch.float64, device="cuda")
+    slab_ms[rank] = own_ms
+    if world > 1:
+        dist.all_reduce(slab_ms)
     t = torch.tensor([ms, ms_e2e, float(rays), float(shadow_rays[0]), float(shadow_rays[1]), float(n_px), float(n_diffuse)],
                      dtype=torch.float64, device="cuda")
     if world > 1:
@@ -357,6 +362,7 @@ def run_cuda(args):
                                           "kernels": passes, "ms_per_frame": round(res_ms, 4)},
             "kernels": kern,
             "pixels": {"slab": n_px, "diffuse": n_diffuse},
+            "slab_kernel_ms": [round(x, 4) for x in slab_ms.tolist()],  # per rank: sum of its own kernels per frame
             "bvh": {k: stats[k] for k in ("n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes")},
         }
         if world == 1 and not args.no_cpu_baseline:
