@@ -212,6 +212,7 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     const crt_visibility* vis = (const crt_visibility*)b->visibility.data;
     const uint32_t n_lights = (uint32_t)bsize(lights);
     const SoaStore T = soa(b->temporal, n);
+#if !defined(CRT_MUTATION_KEEP_TRACED)  // (a mutation build for tests/test_gpu_parity.py: the geometry test must then fail)
     if (geom->serial != ctx->history_serial || b->temporal.data != ctx->history_buffer)
     {
         // another geometry (or another history buffer) than last frame's: its traced marks are not ours to trust
@@ -221,6 +222,7 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
         ctx->history_serial = geom->serial;
         ctx->history_buffer = b->temporal.data;
     }
+#endif
     const dim3 grid = tile_grid(W, rows);
     const bool exact = ctx->math_mode == CRT_MATH_EXACT;
     const HaloPeers peers = halo_peers(ctx, 0, rows, true, n);

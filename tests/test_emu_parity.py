@@ -285,6 +285,33 @@ def test_resolve_reuses_traced_visibility(emu, port):
     emu.geom_free(ge)
 
 
+def test_fused_frame_follows_a_moving_camera(emu, port):
+    """the reference keeps its reservoirs when the camera moves (only the accumulation is cleared,
+    10_restir_di.cpp:257-267): history then holds samples whose origin is another surface — the fused frame must
+    neither reuse their traced visibility in resolve nor lose the merge order"""
+    tris = lit_blocks_ao()
+    W, H = 96, 54
+    opt = orc.make_options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    g = port.geom_build(tris)
+    ge = emu.geom_build(tris)
+    ch = orc.RestirChain(port, W, H, tris, g, *CAM_AO, opt)
+    fu = EmuFusedFrame(emu, W, H, tris, ge, *CAM_AO, opt)
+    cams = [CAM_AO, CAM_AO, ((8.5, 7.5, 8.0), (0.0, 0.5, 0.0)), ((8.5, 7.5, 8.0), (0.0, 0.5, 0.0)), CAM_AO, CAM_AO]
+    for i, (eye, ctr) in enumerate(cams):
+        for o, drv in ((port, ch), (emu, fu)):
+            drv.eye = np.asarray(eye, np.float32)
+            drv.rg = o.lookat(eye, ctr, W, H)
+        ch.step()
+        fu.step()
+        d = diffuse_mask(ch.vis, tris)
+        assert same(ch.vis["index"], fu.vis["index"]), i
+        assert reservoir_mismatch(ch.temporal, fu.aos(fu.T)) == 0, i
+        assert reservoir_mismatch(ch.out[d], fu.output()[d]) == 0, i
+        assert same(ch.accum, fu.accum), i
+    port.geom_free(g)
+    emu.geom_free(ge)
+
+
 def test_soa_aos_round_trip(emu):
     rng = np.random.default_rng(5)
     n = 1000

@@ -449,6 +449,48 @@ def test_resolve_reuse_of_traced_visibility_changes_no_bit(rt):
         rt0.close()
 
 
+def test_fused_frame_with_camera_move_and_new_geometry(rt, port):
+    """History survives a camera move and a geometry replacement in the reference (it only clears the accumulation on
+    a move, 10_restir_di.cpp:257-267, and never rebuilds).  The fused frame's traced-visibility marks must not outlive
+    the geometry they were traced against, and a moved camera must not find 'its own' origin in old samples: exact-math
+    chain vs oracle across both events."""
+    tris_b = lit_blocks_ao()
+    tris_a = tris_b.copy()
+    # the sequence starts with half of the blocks far away and then they arrive (geometry b): samples that were visible
+    # become occluded, which is the case a stale traced mark would get wrong; the lights are the same in both
+    tris_a["vertices"][140:1600] += np.float32(500.0)
+    W, H = 160, 90
+    kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    opt = orc.make_options(**kw)
+    rt.set_math_mode(cedecrt.MATH_EXACT)
+    port.set_math_mode(1)
+    try:
+        ga, gb = port.geom_build(tris_a), port.geom_build(tris_b)
+        ch = orc.RestirChain(port, W, H, tris_a, ga, *CAM_AO, opt)
+        app = cedecrt.RestirDI(rt, W, H, tris_a, *CAM_AO, cedecrt.Options(**kw), fused=True)
+        d_tris_b = rt.to_device(tris_b)
+        geom_b = rt.build_geometry(d_tris_b)
+        cam2 = ((8.5, 7.5, 8.0), (0.0, 0.5, 0.0))
+        steps = [("a", CAM_AO), ("a", CAM_AO), ("a", cam2), ("a", cam2), ("b", cam2), ("b", cam2), ("b", CAM_AO)]
+        for i, (which, (eye, ctr)) in enumerate(steps):
+            ch.eye, ch.rg = np.asarray(eye, np.float32), port.lookat(eye, ctr, W, H)
+            app.eye, app.raygen = tuple(float(np.float32(v)) for v in eye), cedecrt.lookat(eye, ctr, W, H)
+            if which == "b":
+                ch.tris, ch.g = tris_b, gb
+                app.triangles, app.geom = d_tris_b, geom_b
+            ch.step()
+            app.frame()
+            acc = app.accumulation.to_host().view(np.float32).reshape(-1, 4)
+            assert same(app.visibility.to_host()["index"], ch.vis["index"]), i
+            assert same(acc, ch.accum), i
+            assert reservoir_mismatch(ch.temporal, app.export_aos(app.temporal)) == 0, i
+        port.geom_free(ga)
+        port.geom_free(gb)
+    finally:
+        rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+        port.set_math_mode(0)
+
+
 def test_reservoir_layout_round_trip(rt):
     n_w, n_h = 64, 16
     n = n_w * n_h
