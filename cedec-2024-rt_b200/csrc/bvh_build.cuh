@@ -433,6 +433,36 @@ CRT_HD uint8_t quant_exponent(float extent)
     return (uint8_t)(e + 127);
 }
 
+// the node's quantisation grid from its box: power-of-two cell per axis, origin one cell below the box so that the
+// lower margin never needs clamping
+struct NodeGrid
+{
+    float lo[3], inv_cell[3];
+};
+CRT_HD NodeGrid set_node_grid(WideNode& wn, const Aabb& nb)
+{
+    wn.ex = quant_exponent(nb.hi.x - nb.lo.x);
+    wn.ey = quant_exponent(nb.hi.y - nb.lo.y);
+    wn.ez = quant_exponent(nb.hi.z - nb.lo.z);
+    const float cell[3] = {u2f((uint32_t)wn.ex << 23), u2f((uint32_t)wn.ey << 23), u2f((uint32_t)wn.ez << 23)};
+    wn.px = nb.lo.x - cell[0];
+    wn.py = nb.lo.y - cell[1];
+    wn.pz = nb.lo.z - cell[2];
+    return NodeGrid{{wn.px, wn.py, wn.pz}, {1.0f / cell[0], 1.0f / cell[1], 1.0f / cell[2]}};
+}
+// child box -> the slot's six bytes: outward rounding plus kQuantMargin cells of slack (see bvh.cuh: byte_to_unit_float)
+CRT_HD void quantise_slot(WideNode& wn, int s, const Aabb& box, const NodeGrid& g)
+{
+    const float clo[3] = {box.lo.x, box.lo.y, box.lo.z}, chi[3] = {box.hi.x, box.hi.y, box.hi.z};
+    for (int a = 0; a < 3; a++)
+    {
+        const float ql = floorf((clo[a] - g.lo[a]) * g.inv_cell[a] - kQuantMargin);
+        const float qh = ceilf((chi[a] - g.lo[a]) * g.inv_cell[a] + kQuantMargin);
+        wn.qlo[a][s] = (uint8_t)fminf(fmaxf(ql, 0.0f), 255.0f);
+        wn.qhi[a][s] = (uint8_t)fminf(fmaxf(qh, 0.0f), 255.0f);
+    }
+}
+
 CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint32_t* sorted_idx, const BinTree& bt,
                           const WideOut& out)
 {
@@ -527,15 +557,7 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
     for (int k = 0; k < cnt; k++) child_in_slot[slot_of[k]] = k;
 
     WideNode wn;
-    wn.ex = quant_exponent(nb.hi.x - nb.lo.x);
-    wn.ey = quant_exponent(nb.hi.y - nb.lo.y);
-    wn.ez = quant_exponent(nb.hi.z - nb.lo.z);
-    const float cell[3] = {u2f((uint32_t)wn.ex << 23), u2f((uint32_t)wn.ey << 23), u2f((uint32_t)wn.ez << 23)};
-    const float inv_cell[3] = {1.0f / cell[0], 1.0f / cell[1], 1.0f / cell[2]};
-    // grid origin one cell below the box, so that the lower margin never needs clamping
-    wn.px = nb.lo.x - cell[0];
-    wn.py = nb.lo.y - cell[1];
-    wn.pz = nb.lo.z - cell[2];
+    const NodeGrid grid = set_node_grid(wn, nb);
 
     uint32_t n_inner = 0, n_leaf_tris = 0;
     uint8_t imask = 0;
@@ -558,7 +580,6 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
     wn.tri_base = tri_base;
 
     uint32_t inner_rank = 0, tri_off = 0;
-    const float nlo[3] = {wn.px, wn.py, wn.pz};
     for (int s = 0; s < 8; s++)
     {
         const int k = child_in_slot[s];
@@ -572,15 +593,7 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
             }
             continue;
         }
-        const float clo[3] = {cb[k].lo.x, cb[k].lo.y, cb[k].lo.z}, chi[3] = {cb[k].hi.x, cb[k].hi.y, cb[k].hi.z};
-        for (int a = 0; a < 3; a++)
-        {
-            // outward rounding plus kQuantMargin cells of slack (see bvh.cuh: byte_to_unit_float)
-            const float ql = floorf((clo[a] - nlo[a]) * inv_cell[a] - kQuantMargin);
-            const float qh = ceilf((chi[a] - nlo[a]) * inv_cell[a] + kQuantMargin);
-            wn.qlo[a][s] = (uint8_t)fminf(fmaxf(ql, 0.0f), 255.0f);
-            wn.qhi[a][s] = (uint8_t)fminf(fmaxf(qh, 0.0f), 255.0f);
-        }
+        quantise_slot(wn, s, cb[k], grid);
         const uint32_t tc = bin_tri_count(bt, ch[k]);
         if (!ch_leaf[k])
         {
@@ -607,5 +620,56 @@ CRT_HD void collapse_item(const CollapseItem it, const float* tris60, const uint
         }
     }
     out.nodes[it.wnode] = wn;
+}
+
+// ---- refit (crt_refit_geometry; HIPRT's hiprtBuildOperationUpdate, hiprt_types.h:131-135): the vertices moved, the
+// topology stays.  Triangle records reload their vertices; nodes recompute their grids and child bytes bottom-up, one
+// launch per level (the collapse allocated node indices level by level, so a level is an index range).  Slot
+// assignment, child indices and triangle ranges are kept: traversal order may be less front-to-back than a fresh
+// build's, results are the same (the tree only culls).
+CRT_HD void refit_tri(uint32_t i, const float* tris60, WideTri* tris)
+{
+    WideTri wt = tris[i];
+    const BuildTri t = load_build_tri(tris60, (uint32_t)wt.prim);
+    wt.v0x = t.v0.x; wt.v0y = t.v0.y; wt.v0z = t.v0.z;
+    wt.v1x = t.v1.x; wt.v1y = t.v1.y; wt.v1z = t.v1.z;
+    wt.v2x = t.v2.x; wt.v2y = t.v2.y; wt.v2z = t.v2.z;
+    tris[i] = wt;
+}
+// node_box: [n_nodes][6] exact (padded) boxes; the children's entries are final when their parent's level runs
+CRT_HD void refit_node(uint32_t node, WideNode* nodes, const WideTri* tris, float* node_box, float pad)
+{
+    WideNode wn = nodes[node];
+    Aabb cb[8], nb;
+    bool any = false;
+    for (int s = 0; s < 8; s++)
+    {
+        const uint32_t meta = wn.meta[s];
+        if (meta == 0) continue;
+        Aabb b;
+        if ((meta & 0x1fu) >= 24u)  // inner child
+            b = load_box(node_box, wn.child_base + (uint32_t)popc((uint32_t)wn.imask & ((1u << s) - 1u)));
+        else
+        {
+            const uint32_t count = (uint32_t)popc(meta >> 5), first = wn.tri_base + (meta & 0x1fu);
+            for (uint32_t j = 0; j < count; j++)
+            {
+                const WideTri& w = tris[first + j];
+                const Aabb tb = tri_aabb(BuildTri{{w.v0x, w.v0y, w.v0z}, {w.v1x, w.v1y, w.v1z}, {w.v2x, w.v2y, w.v2z}});
+                b = j ? aabb_union(b, tb) : tb;
+            }
+            b.lo = b.lo - f3{pad, pad, pad};
+            b.hi = b.hi + f3{pad, pad, pad};
+        }
+        cb[s] = b;
+        nb = any ? aabb_union(nb, b) : b;
+        any = true;
+    }
+    if (!any) return;  // the empty tree's root
+    const NodeGrid grid = set_node_grid(wn, nb);
+    for (int s = 0; s < 8; s++)
+        if (wn.meta[s] != 0) quantise_slot(wn, s, cb[s], grid);
+    nodes[node] = wn;
+    store_box(node_box, node, nb);
 }
 }  // namespace crt

@@ -61,6 +61,10 @@ struct crt_geometry_t
     const void* light_table_key = nullptr;
     size_t light_table_n = 0;
     float postpone_ratio = crt::kPostponeRatio;
+    // refit (crt_refit_geometry): first node of every level of the wide tree, exact node boxes (allocated on demand)
+    std::vector<uint32_t> level_begin;
+    float* node_box = nullptr;
+    float refit_ms = 0.0f;
     crt::Bvh view() const { return crt::Bvh{nodes, tris, postpone_ratio}; }
 };
 

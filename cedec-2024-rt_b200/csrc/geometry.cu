@@ -280,9 +280,11 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
     CollapseItem* q_out = m_q1.as<CollapseItem>();
     uint32_t n_items = 1;
     int depth = 0;
+    g->level_begin.assign(1, 0u);
     while (n_items)
     {
         depth++;
+        g->level_begin.push_back(g->level_begin.back() + n_items);  // this level's nodes end where the next level's begin
         out.next = q_out;
         CRT_CUDA(cudaMemsetAsync(out.next_count, 0, sizeof(uint32_t), st));
         k_collapse<<<div_up(n_items, kBuildBlock), kBuildBlock, 0, st>>>(n_items, q_in, tris60, sorted_idx, bt, out);
@@ -321,6 +323,63 @@ static int build(crt_ctx* ctx, const crt_triangle* d_tris, size_t n_sz, crt_geom
         set_error("wide BVH depth %d exceeds the traversal stack (%d entries, two per level)", depth, kStackSize);
         return CRT_ESTACK;
     }
+    return CRT_OK;
+}
+
+// ---- refit
+__global__ void __launch_bounds__(kBuildBlock) k_refit_tris(uint32_t n, const float* tris60, WideTri* tris)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) refit_tri(i, tris60, tris);
+}
+__global__ void __launch_bounds__(kBuildBlock)
+    k_refit_nodes(uint32_t first, uint32_t count, WideNode* nodes, const WideTri* tris, float* node_box, float pad)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) refit_node(first + i, nodes, tris, node_box, pad);
+}
+static std::atomic<unsigned long long> g_next_serial{1};
+
+static int refit(crt_ctx* ctx, crt_geometry_t* g)
+{
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)g->n_tris;
+    if (n == 0) return CRT_OK;
+    const float* tris60 = (const float*)g->src;
+    cudaEvent_t e0, e1;
+    CRT_CUDA(cudaEventCreate(&e0));
+    CRT_CUDA(cudaEventCreate(&e1));
+    CRT_CUDA(cudaEventRecord(e0, st));
+    // the padding follows the largest coordinate (build(), step 1)
+    DevMem m_bounds;
+    CRT_ALLOC(m_bounds, 6 * sizeof(uint32_t));
+    k_init_bounds<<<1, kBuildBlock, 0, st>>>(m_bounds.as<uint32_t>());
+    k_tri_bounds<<<div_up(n, kBuildBlock), kBuildBlock, 0, st>>>(n, tris60, m_bounds.as<uint32_t>());
+    uint32_t hb[6];
+    CRT_CUDA(cudaMemcpyAsync(hb, m_bounds.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CRT_CUDA(cudaStreamSynchronize(st));
+    float max_abs = 0.0f;
+    for (int a = 0; a < 6; a++) max_abs = fmaxf(max_abs, fabsf(ordered_to_float(hb[a])));
+    float pad_scale = 64.0f;
+    if (const char* s = getenv("CRT_BVH_PAD_ULPS")) pad_scale = (float)atof(s);
+    g->pad = pad_scale * 5.9604645e-8f * fmaxf(max_abs, 1.0f);
+    if (!g->node_box) CRT_CUDA(cudaMalloc((void**)&g->node_box, g->n_nodes * 6 * sizeof(float)));
+    k_refit_tris<<<div_up(n, kBuildBlock), kBuildBlock, 0, st>>>(n, tris60, g->tris);
+    const int levels = (int)g->level_begin.size() - 1;
+    for (int l = levels - 1; l >= 0; l--)
+    {
+        const uint32_t first = g->level_begin[l], count = g->level_begin[l + 1] - first;
+        if (count) k_refit_nodes<<<div_up(count, kBuildBlock), kBuildBlock, 0, st>>>(first, count, g->nodes, g->tris, g->node_box, g->pad);
+    }
+    CRT_CUDA(cudaEventRecord(e1, st));
+    CRT_CUDA(cudaStreamSynchronize(st));
+    CRT_CUDA(cudaEventElapsedTime(&g->refit_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CRT_CUDA(cudaGetLastError());
+    ctx->launches += 3 + levels;
+    g->serial = g_next_serial.fetch_add(1);  // visibility traced against the old positions is history (kernels_fast.cu)
+    g->light_table_key = nullptr;            // emissive triangles may have moved: the light records are rebuilt on use
     return CRT_OK;
 }
 
@@ -397,8 +456,7 @@ extern "C" int crt_build_geometry(crt_ctx* ctx, const crt_triangle* d_triangles,
     CRT_REQUIRE(n < 0x7fffffffull, "too many triangles");
     CRT_CUDA(cudaSetDevice(ctx->device));
     crt_geometry_t* g = new crt_geometry_t;
-    static std::atomic<unsigned long long> next_serial{1};
-    g->serial = next_serial.fetch_add(1);
+    g->serial = g_next_serial.fetch_add(1);
     const int rc = build(ctx, d_triangles, n, g);
     if (rc != CRT_OK)
     {
@@ -412,6 +470,14 @@ extern "C" int crt_build_geometry(crt_ctx* ctx, const crt_triangle* d_triangles,
     return CRT_OK;
 }
 
+extern "C" int crt_refit_geometry(crt_ctx* ctx, crt_geometry g)
+{
+    CRT_REQUIRE(ctx && g, "null context or geometry");
+    CRT_REQUIRE(g->device == ctx->device, "geometry belongs to another device");
+    CRT_CUDA(cudaSetDevice(ctx->device));
+    return refit(ctx, g);
+}
+
 extern "C" int crt_destroy_geometry(crt_ctx* ctx, crt_geometry g)
 {
     CRT_REQUIRE(ctx, "null context");
@@ -419,6 +485,7 @@ extern "C" int crt_destroy_geometry(crt_ctx* ctx, crt_geometry g)
     CRT_CUDA(cudaSetDevice(g->device));
     CRT_CUDA(cudaFree(g->nodes));
     CRT_CUDA(cudaFree(g->tris));
+    if (g->node_box) CRT_CUDA(cudaFree(g->node_box));
     if (g->light_table) CRT_CUDA(cudaFree(g->light_table));
     delete g;
     return CRT_OK;
@@ -434,7 +501,7 @@ extern "C" int crt_geometry_stats(crt_geometry g, double out[8])
     out[4] = (double)(g->n_nodes * sizeof(WideNode));
     out[5] = (double)(g->n_tris * sizeof(WideTri));
     out[6] = (double)g->pad;
-    out[7] = 0.0;
+    out[7] = (double)g->refit_ms;
     return CRT_OK;
 }
 

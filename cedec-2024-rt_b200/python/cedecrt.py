@@ -135,6 +135,7 @@ def _load():
         "crt_profile_end": [P, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), I, C.POINTER(I)],
         "crt_build_geometry": [P, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)],
         "crt_destroy_geometry": [P, G],
+        "crt_refit_geometry": [P, G],
         "crt_geometry_stats": [G, C.POINTER(C.c_double)],
         "crt_trace_closest": [P, G, C.c_size_t, C.c_void_p, C.c_void_p, F, F, C.c_void_p, C.c_void_p],
         "crt_trace_any": [P, G, C.c_size_t, C.c_void_p, C.c_void_p, F, F, C.c_void_p],
@@ -268,8 +269,12 @@ class Geometry:
     def stats(self):
         out = (C.c_double * 8)()
         self.rt._check(self.rt.lib.crt_geometry_stats(self.handle, out))
-        keys = ("n_tris", "n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes", "pad")
+        keys = ("n_tris", "n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes", "pad", "refit_ms")
         return dict(zip(keys, list(out)))
+
+    def refit(self):
+        """the vertices of `triangles` changed on the device (same count and order): update the tree in place"""
+        self.rt._check(self.rt.lib.crt_refit_geometry(self.rt.ctx, self.handle))
 
     def destroy(self):
         if self.handle:

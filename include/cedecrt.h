@@ -127,7 +127,12 @@ void crt_raygen_lookat(crt_raygen* rg, const float eye[3], const float center[3]
  * to the kernels in hiprtGeometry's slot. */
 int crt_build_geometry(crt_ctx* ctx, const crt_triangle* d_triangles, size_t n, crt_geometry* out);
 int crt_destroy_geometry(crt_ctx* ctx, crt_geometry g);
-/* build statistics: {n_tris, n_wide_nodes, max_depth, build_ms, node_bytes, tri_bytes, sah_cost*1000} */
+/* The host has moved vertices in the triangle array the tree was built over (same count, same order): bring the tree
+ * up to date without rebuilding it — HIPRT's hiprtBuildOperationUpdate (libs/hiprt/hiprt/hiprt_types.h:131-135), which
+ * the reference never calls (it builds once, loader.hpp:106-110).  Topology is kept, boxes are recomputed bottom-up;
+ * hits stay exact (the tree only culls).  Synchronous. */
+int crt_refit_geometry(crt_ctx* ctx, crt_geometry g);
+/* statistics: {n_tris, n_wide_nodes, max_depth, build_ms, node_bytes, tri_bytes, box padding, last refit_ms} */
 int crt_geometry_stats(crt_geometry g, double out[8]);
 /* single-ray probes for tests (device arrays of n rays: origin, direction as float3, tmin/tmax);
  * closest: out_prim (-1 = miss), out_tuv (t,u,v) — tie rule: smallest t, then largest primitive id

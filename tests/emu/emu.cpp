@@ -58,6 +58,7 @@ struct EmuGeom
     const float* tris60 = nullptr;
     int depth = 0;
     float pad = 0;
+    std::vector<uint32_t> level_begin;  // csrc/geometry.cu: crt_geometry_t::level_begin
     Bvh view() const { return Bvh{nodes.data(), tris.data(), kPostponeRatio}; }
 };
 int g_math_mode = 0;
@@ -154,9 +155,11 @@ EmuGeom* build(const float* tris60, uint32_t n)
     q0[0] = CollapseItem{0u, 0u};
     uint32_t n_items = 1;
     CollapseItem *qi = q0.data(), *qo = q1.data();
+    g->level_begin.assign(1, 0u);
     while (n_items)
     {
         g->depth++;
+        g->level_begin.push_back(g->level_begin.back() + n_items);
         out.next = qo;
         counters[2] = 0;
         for (uint32_t i = 0; i < n_items; i++) collapse_item(qi[i], tris60, idx.data(), bt, out);
@@ -190,6 +193,22 @@ extern "C"
     void orc_set_range(long b, long e) { g_tid_begin = b; g_tid_end = e; }
     void* orc_geom_build(const crt_triangle* tris, int n) { return build((const float*)tris, (uint32_t)n); }
     void orc_geom_free(void* g) { delete (EmuGeom*)g; }
+    // same sequence as csrc/geometry.cu:refit() — the caller has changed vertices of the array the tree was built over
+    void emu_geom_refit(void* gp)
+    {
+        EmuGeom* g = (EmuGeom*)gp;
+        const uint32_t n = (uint32_t)g->tris.size();
+        if (g->level_begin.empty()) return;  // the empty tree
+        float max_abs = 0;
+        for (size_t i = 0; i < (size_t)n * 15; i++)
+            if (i % 15 < 9) max_abs = fmaxf(max_abs, fabsf(g->tris60[i]));
+        g->pad = 64.0f * 5.9604645e-8f * fmaxf(max_abs, 1.0f);
+        std::vector<float> node_box(g->nodes.size() * 6);
+        for (uint32_t i = 0; i < n; i++) refit_tri(i, g->tris60, g->tris.data());
+        for (int l = (int)g->level_begin.size() - 2; l >= 0; l--)
+            for (uint32_t i = g->level_begin[l]; i < g->level_begin[l + 1]; i++)
+                refit_node(i, g->nodes.data(), g->tris.data(), node_box.data(), g->pad);
+    }
     void emu_geom_stats(void* gp, double* out)
     {
         EmuGeom* g = (EmuGeom*)gp;

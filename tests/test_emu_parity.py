@@ -162,6 +162,28 @@ def test_degenerate_inputs(emu, port):
         assert same(outs[0]["index"], outs[1]["index"]) and same(outs[0]["uv"], outs[1]["uv"])
 
 
+def test_refit_after_moving_vertices(emu, port):
+    """crt_refit_geometry's device functions (bvh_build.cuh: refit_tri / refit_node): after vertices move, the
+    refitted tree gives the closest hits of a tree built from scratch — the oracle's — bit for bit"""
+    tris = small_scene("blocks_ao").copy()
+    W, H = 128, 72
+    ge = emu.geom_build(tris)
+    rng = np.random.default_rng(3)
+    for step in range(2):
+        # whole blocks slide, single vertices jitter, and the scene box grows
+        tris["vertices"][300:900] += rng.uniform(-1.5, 1.5, 3).astype(np.float32)
+        tris["vertices"][1200:1300] += rng.uniform(-0.05, 0.05, (100, 3, 3)).astype(np.float32)
+        tris["vertices"][2000:2012] += np.float32(25.0 * (step + 1))
+        emu.lib.emu_geom_refit(ge)
+        g = port.geom_build(tris)
+        rg = port.lookat(*CAM_AO, W, H)
+        a, b = port.raycast(W, H, g, tris, rg), emu.raycast(W, H, ge, tris, rg)
+        assert same(a["index"], b["index"]) and same(a["uv"], b["uv"]), step
+        assert (a["index"] >= 0).sum() > 1000
+        port.geom_free(g)
+    emu.geom_free(ge)
+
+
 # ---------------------------------------------------------------------------------------------- fused frame
 class EmuFusedFrame:
     """Drives emu_restir_frame_fast (the kernel sequence of crt_restir_di_frame, csrc/kernels_fast.cu) on planar
