@@ -20,7 +20,20 @@
 // per-kernel path of kernels_dropin.cu on AoS buffers instead — same results, reference data flow.
 #include "launch_common.cuh"
 
+// This file is compiled twice (csrc/Makefile).  The regular object carries the host API and the per-pixel kernels in
+// namespace crt::ex, compiled like the rest of the library (-fmad=false, IEEE division and square root: the arithmetic
+// the CPU oracle checks bit for bit).  The second object (-DCRT_FASTMATH_TU -use_fast_math) carries only the per-pixel
+// kernels again, in namespace crt::fm: CRT_MATH_FAST.  Traversal and the triangle test are not in these kernels
+// (shadow rays are queued, primary rays are k_raycast), so they stay exact in every mode.
+#if defined(CRT_FASTMATH_TU)
+#define CRT_KNS fm
+#else
+#define CRT_KNS ex
+#endif
+
 namespace crt
+{
+namespace CRT_KNS
 {
 #ifndef CRT_CT_MINBLOCKS
 #define CRT_CT_MINBLOCKS 3  // 80 registers; measured best with kRisBatch = 2 (profiles/r1/tuning_j.txt)
@@ -64,6 +77,51 @@ __global__ void __launch_bounds__(256)
     r.rx = sh.rad.x; r.ry = sh.rad.y; r.rz = sh.rad.z;
     queue_push(q, d.want, r);
 }
+
+// host-side launchers, one set per namespace (the API below picks the namespace from the context's math mode)
+void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
+                               const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
+                               const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
+                               ShadowQueue q, HaloPeers peers)
+{
+    if (table)
+    {
+        const LightsTable L{table, n_lights};
+        auto k = exact ? k_candidate_temporal<LightsTable, 1> : k_candidate_temporal<LightsTable, 0>;
+        k<<<grid, 256, 0, st>>>(W, H, rows, frame, bvh, tris60, vis, eye, L, options, T, g, q, peers);
+    }
+    else
+    {
+        const LightsIndexed L{tris60, light_ids, n_lights};
+        auto k = exact ? k_candidate_temporal<LightsIndexed, 1> : k_candidate_temporal<LightsIndexed, 0>;
+        k<<<grid, 256, 0, st>>>(W, H, rows, frame, bvh, tris60, vis, eye, L, options, T, g, q, peers);
+    }
+}
+void launch_spatial(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye,
+                    crt_options options, SoaStore in, SoaStore out, GBuf g, HaloPeers peers)
+{
+    auto k = exact ? k_spatial_fast<1> : k_spatial_fast<0>;
+    k<<<grid, 256, 0, st>>>(W, H, rows, frame, pass, bvh, eye, options, in, out, g, peers);
+}
+void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H, Rows rows, const float* tris60,
+                    const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q, int accumulate, int reuse_traced)
+{
+    k_resolve_fast<<<grid, 256, 0, st>>>(accum, W, H, rows, tris60, vis, res, g, q, accumulate, reuse_traced);
+}
+}  // namespace CRT_KNS
+
+#if !defined(CRT_FASTMATH_TU)
+namespace fm
+{
+void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
+                               const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
+                               const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
+                               ShadowQueue q, HaloPeers peers);
+void launch_spatial(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye,
+                    crt_options options, SoaStore in, SoaStore out, GBuf g, HaloPeers peers);
+void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H, Rows rows, const float* tris60,
+                    const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q, int accumulate, int reuse_traced);
+}  // namespace fm
 // the traced marks of a history buffer stop being true when the geometry they were traced against is replaced
 __global__ void __launch_bounds__(256) k_clear_traced(size_t n, SoaStore s)
 {
@@ -83,8 +141,10 @@ __global__ void __launch_bounds__(256) k_aos_to_soa(size_t n, const crt_reservoi
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) aos_to_soa(aos, s, (int)i);
 }
+#endif  // !CRT_FASTMATH_TU (the namespace closes in both builds)
 }  // namespace crt
 
+#if !defined(CRT_FASTMATH_TU)
 using namespace crt;
 
 namespace
@@ -226,21 +286,15 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     const dim3 grid = tile_grid(W, rows);
     const bool exact = ctx->math_mode == CRT_MATH_EXACT;
     const HaloPeers peers = halo_peers(ctx, 0, rows, true, n);
+    const LightRec* table = nullptr;
     if (ctx->light_table)
     {
-        const LightRec* table = nullptr;
         rc = light_table_for(ctx, geom, tris60, (const uint32_t*)lights.data, n_lights, &table);
         if (rc != CRT_OK) return rc;
-        const LightsTable L{table, n_lights};
-        auto k = exact ? k_candidate_temporal<LightsTable, 1> : k_candidate_temporal<LightsTable, 0>;
-        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q, peers);
     }
-    else
-    {
-        const LightsIndexed L{tris60, (const uint32_t*)lights.data, n_lights};
-        auto k = exact ? k_candidate_temporal<LightsIndexed, 1> : k_candidate_temporal<LightsIndexed, 0>;
-        k<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), L, options, T, g, q, peers);
-    }
+    (ctx->math_mode == CRT_MATH_FAST ? fm::launch_candidate_temporal : ex::launch_candidate_temporal)(
+        ctx->stream, exact, grid, W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), table,
+        (const uint32_t*)lights.data, n_lights, options, T, g, q, peers);
     rc = check_launch(ctx, "candidate_temporal");
     if (rc != CRT_OK || !options.use_visibility_reuse) return rc;
     ShadowSink sink{nullptr, nullptr, 0, (uint32_t*)T.plane(0, 0)};
@@ -274,10 +328,11 @@ extern "C" int crt_restir_spatial_pass(crt_ctx* ctx, int W, int H, int frame, in
     if (rc != CRT_OK) return rc;
     crt_buffer in, out;
     pass_buffers(b, pass, &in, &out);
-    auto k = ctx->math_mode == CRT_MATH_EXACT ? k_spatial_fast<1> : k_spatial_fast<0>;
     // the last pass's output is only read by this rank's resolve: nothing to mirror
     const HaloPeers peers = pass + 1 < options.spatial_resampling_passes ? halo_peers(ctx, which_of(b, out), rows, false, n) : HaloPeers();
-    k<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(W, H, rows, frame, pass, geom->view(), to_f3(eye), options, soa(in, n), soa(out, n), g, peers);
+    (ctx->math_mode == CRT_MATH_FAST ? fm::launch_spatial : ex::launch_spatial)(
+        ctx->stream, ctx->math_mode == CRT_MATH_EXACT, tile_grid(W, rows), W, H, rows, frame, pass, geom->view(), to_f3(eye),
+        options, soa(in, n), soa(out, n), g, peers);
     return check_launch(ctx, "spatial_fast");
 }
 
@@ -306,9 +361,10 @@ extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geo
     rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
     if (rc != CRT_OK) return rc;
     crt_float4* accum = (crt_float4*)b->accumulation.data;
-    k_resolve_fast<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(accum, W, H, rows, (const float*)triangles.data,
-                                                               (const crt_visibility*)b->visibility.data, soa(fin, n), g, q,
-                                                               options.accumulate, ctx->resolve_reuse && options.use_visibility_reuse);
+    (ctx->math_mode == CRT_MATH_FAST ? fm::launch_resolve : ex::launch_resolve)(
+        ctx->stream, tile_grid(W, rows), accum, W, H, rows, (const float*)triangles.data,
+        (const crt_visibility*)b->visibility.data, soa(fin, n), g, q, options.accumulate,
+        ctx->resolve_reuse && options.use_visibility_reuse);
     rc = check_launch(ctx, "resolve_fast");
     if (rc != CRT_OK) return rc;
     rc = queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr});
@@ -350,3 +406,4 @@ extern "C" int crt_reservoir_import_aos(crt_ctx* ctx, int W, int H, crt_buffer a
     k_aos_to_soa<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (const crt_reservoir*)aos_in.data, soa(soa_storage, n));
     return check_launch(ctx, "aos_to_soa");
 }
+#endif  // !CRT_FASTMATH_TU

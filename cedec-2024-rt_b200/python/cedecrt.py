@@ -28,7 +28,7 @@ RESERVOIR = np.dtype(  # reservoir.hpp:5-38
 FLOAT4 = np.dtype((np.float32, (4,)))
 assert TRIANGLE.itemsize == 60 and VISIBILITY.itemsize == 16 and RESERVOIR.itemsize == 76
 
-MATH_LIBDEVICE, MATH_EXACT = 0, 1
+MATH_LIBDEVICE, MATH_EXACT, MATH_FAST = 0, 1, 2
 
 
 class Float3(C.Structure):
