@@ -483,6 +483,29 @@ def test_fused_equals_per_kernel_path_default_math(rt, scene):
     assert float(a.accumulation.to_host().view(np.float32).reshape(-1, 4)[:, :3].sum()) > 0
 
 
+def test_fused_equals_per_kernel_path_at_full_size(rt):
+    """BASELINE config 5 at full size (blocks_restir x6 = 9.6 M triangles, 3840x2160, temporal + 3 spatial passes +
+    visibility reuse): the fused frame bench.py times and the reference's launch list give the same images, bit for
+    bit, over three frames — the launch list being the path the small-size tests tie to the oracle kernel by kernel."""
+    import scenes
+
+    tris = scenes.tile_scene(staged("blocks_restir"), 3, 2, 130.0, 82.0)
+    W, H = 3840, 2160
+    kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    a = cedecrt.RestirDI(rt, W, H, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=False)
+    b = cedecrt.RestirDI(rt, W, H, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
+    for f in range(3):
+        a.frame()
+        b.frame()
+        assert same(a.accumulation.to_host(), b.accumulation.to_host()), f
+    assert same(a.visibility.to_host(), b.visibility.to_host())
+    assert same(a.pixels.to_host(), b.pixels.to_host())
+    acc = a.accumulation.to_host().view(np.float32).reshape(-1, 4)
+    assert np.isfinite(acc).all() and float(acc[:, :3].sum()) > 0
+    d = diffuse_mask(a.visibility.to_host(), tris)
+    assert reservoir_mismatch(a.output.to_host()[d], b.output_reservoirs()[d]) == 0
+
+
 def test_resolve_reuse_of_traced_visibility_changes_no_bit(rt):
     """resolve skips the shadow rays whose answer the reservoir already carries (restir_fast.cuh: kTracedBit); a
     context created with CRT_RESOLVE_REUSE=0 traces every resolve ray like the reference.  Same images, fewer rays."""
