@@ -483,6 +483,46 @@ def test_fused_equals_per_kernel_path_default_math(rt, scene):
     assert float(a.accumulation.to_host().view(np.float32).reshape(-1, 4)[:, :3].sum()) > 0
 
 
+def test_full_size_band_bit_exact_vs_oracle(rt, port):
+    """BASELINE config 5 itself against the oracle: blocks_restir x6 (9 590 208 triangles, 875 892 lights), 3840x2160,
+    exact math.  The CPU oracle computes a band of 560 image rows of frames 1 and 2 (every kernel of the loop restricted
+    to the band); 3 spatial passes reach 3 x 87 rows, so the 32 central rows of the band see exactly what the full
+    frame sees — there the fused frame's primitive ids, uv, temporal reservoirs, final reservoirs, accumulation and
+    RGBA8 must equal the oracle's bit for bit."""
+    import scenes
+
+    tris = scenes.tile_scene(staged("blocks_restir"), 3, 2, 130.0, 82.0)
+    W, H, c, half, keep = 3840, 2160, 1080, 280, 16
+    kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    rt.set_math_mode(cedecrt.MATH_EXACT)
+    port.set_math_mode(1)
+    try:
+        g = port.geom_build(tris)
+        ch = orc.RestirChain(port, W, H, tris, g, *CAM_RESTIR, orc.make_options(**kw))
+        app = cedecrt.RestirDI(rt, W, H, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
+        port.set_range((c - half) * W, (c + half) * W)
+        # rows yi in [c - keep, c + keep) of the bottom-up buffers
+        rows = slice((H - (c + keep)) * W, (H - (c - keep)) * W)
+        for f in range(2):
+            ch.step()
+            app.frame()
+            vis = app.visibility.to_host()[rows]
+            assert same(vis["index"], ch.vis["index"][rows]) and same(vis["uv"], ch.vis["uv"][rows]), f
+            acc = app.accumulation.to_host().view(np.float32).reshape(-1, 4)[rows]
+            assert same(acc, ch.accum[rows]), f
+            assert reservoir_mismatch(ch.temporal[rows], app.export_aos(app.temporal)[rows]) == 0, f
+            d = diffuse_mask(ch.vis[rows], tris)
+            assert d.sum() > 50000
+            assert reservoir_mismatch(ch.out[rows][d], app.output_reservoirs()[rows][d]) == 0, f
+        pix = app.pixels.to_host().reshape(-1, 4)[rows]
+        assert same(pix, port.tone_mapping(ch.accum, W, H).reshape(-1, 4)[rows])
+        port.geom_free(g)
+    finally:
+        port.set_range(0, -1)
+        rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+        port.set_math_mode(0)
+
+
 def test_fused_equals_per_kernel_path_at_full_size(rt):
     """BASELINE config 5 at full size (blocks_restir x6 = 9.6 M triangles, 3840x2160, temporal + 3 spatial passes +
     visibility reuse): the fused frame bench.py times and the reference's launch list give the same images, bit for
