@@ -13,8 +13,13 @@ or as the reference's launch list (--mode dropin) — over BASELINE config 5: bl
 value  = W*H*K / device time of the K frames (CUDA events, max over ranks), buffers resident in HBM —
          the reference's own timing convention (OroStopwatch around the kernel list, 10_restir_di.cpp:254,382).
 e2e    = the same loop including, every frame, the device->host copy of the RGBA8 image into pinned host
-         memory (10_restir_di.cpp:386-389); the per-frame host inputs (RayGenerator, eye, Options) travel as
-         kernel parameters.
+         memory (10_restir_di.cpp:386-389) — on a copy stream overlapped with the next frame (--readback pipelined,
+         default) or copy-then-synchronise like the reference (--readback sync); the per-frame host inputs
+         (RayGenerator, eye, Options) travel as kernel parameters.
+fast_math = the same K frames with crt_set_math_mode(CRT_MATH_FAST), reported beside the headline (never as it):
+         reservoir kernels with fast math, rays and triangle tests exact, radiance 6e-5 from the oracle after 64 frames.
+roofline = the dominant kernel by time (a traversal kernel: issue-bound), `traffic` from the
+         committed ncu capture; roofline_reservoir_passes = the reservoir kernels' algorithmic bytes / their time.
 N > 1  : the frame is split into horizontal row slabs, one rank per GPU (strong scaling); scene and BVH are
          replicated; the 87 halo rows of reservoirs the spatial passes read are stored by the producing rank
          directly into its neighbours' buffers over NVLink (--halo p2p, csrc/slab_p2p.cu) or exchanged with
