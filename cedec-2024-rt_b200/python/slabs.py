@@ -6,8 +6,9 @@ except spatial_resampling, which reads the reservoirs and the sky/emissive class
 
   * rank r computes image rows yi in [y0, y1) (crt_set_row_range); buffers are full-size and indices global;
   * before every spatial pass each rank sends the HALO = 87 boundary rows of the pass's input reservoirs to its
-    slab neighbours and receives theirs into the same global positions; once per frame the same happens for the
-    neighbour-rejection data (Visibility rows in drop-in mode, the 1-byte pixel-class plane in fused mode).
+    slab neighbours and receives theirs into the same global positions; in drop-in mode the same happens once per
+    frame for the Visibility rows the neighbour rejection reads (in fused mode the sky/emissive marker travels inside
+    the reservoir records themselves, csrc/restir_fast.cuh: kSkipBit).
 
 Nothing here touches pixel data itself: the functions compute byte ranges of bottom-up buffers
 (pixel_idx = xi + (H - yi - 1) * W, 10_restir_di.cu:18-20) and issue torch.distributed P2P ops on them, so the same
@@ -280,10 +281,6 @@ class SlabRenderer:
             return
         if self.fused:
             rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
-            if self.world > 1:
-                if self.t_cls is None:
-                    self.t_cls = self.torch.as_tensor(CudaArrayView(rt.restir_class_plane(), W * H), device="cuda")
-                self.exchange(self.t_cls, CLASS_PLANE)
             for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
                 self.exchange(self.t_tmp if k == 0 else (self.t_r1 if k % 2 else self.t_r0), SOA_RESERVOIR)
                 rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
