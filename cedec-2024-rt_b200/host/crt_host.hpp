@@ -157,6 +157,9 @@ inline crt_geometry buildGeometry(const crt::Device& dev, const TypedBuffer<crt_
     return g;
 }
 
+// hiprtBuildOperationUpdate (hiprt_types.h:131-135): the host moved vertices in `triangles` (same count and order)
+inline void refitGeometry(const crt::Device& dev, crt_geometry geom) { CRT_CHECKED(crt_refit_geometry(dev.ctx(), geom)); }
+
 // OroStopwatch (OrochiUtils.h:179-209)
 class Stopwatch
 {
