@@ -153,19 +153,23 @@ HBM_BOUND = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampli
              "candidate_temporal", "resolve_fast")
 
 
-from slabs import HALO as HALO_ROWS, SlabRenderer  # noqa: E402  (cedec-2024-rt_b200/python/slabs.py)
+from slabs import HALO as HALO_ROWS, SlabGroup, SlabRenderer  # noqa: E402  (cedec-2024-rt_b200/python/slabs.py)
 
 
-def pixel_classes(torch, r):
-    """(pixels, diffuse pixels) of this rank's slab, from the visibility buffer: a diffuse pixel is one whose
+def pixel_classes(torch, renderer):
+    """(pixels, diffuse pixels) of this rank's slab(s), from the visibility buffer: a diffuse pixel is one whose
     primary hit is a non-emissive surface — the only pixels with reservoir work and shadow rays."""
-    vis = r._rows(r.t_vis, 16, r.y0, r.y1).view(torch.int32).reshape(-1, 4)[:, 2]
-    em = r.t_tris.view(torch.float32).reshape(-1, 15)[:, 12:15]
-    is_em = (em > 0).any(1)
-    hit = vis >= 0
-    diffuse = hit.clone()
-    diffuse[hit] = ~is_em[vis[hit].long()]
-    return r.W * (r.y1 - r.y0), int(diffuse.sum().item())
+    n_px = n_diffuse = 0
+    for r in renderer.slabs:
+        vis = r._rows(r.t_vis, 16, r.y0, r.y1).view(torch.int32).reshape(-1, 4)[:, 2]
+        em = r.t_tris.view(torch.float32).reshape(-1, 15)[:, 12:15]
+        is_em = (em > 0).any(1)
+        hit = vis >= 0
+        diffuse = hit.clone()
+        diffuse[hit] = ~is_em[vis[hit].long()]
+        n_px += r.W * (r.y1 - r.y0)
+        n_diffuse += int(diffuse.sum().item())
+    return n_px, n_diffuse
 
 
 def run_cuda(args):
@@ -193,11 +197,20 @@ def run_cuda(args):
     tris, cam, workload = load_workload()
     W, H = args.width, args.height
     fused = args.mode == "fused"
-    r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
+    # slabs per GPU: 1 by default.  --sub 2 gives every rank two slabs on two streams that fill each other's ramp-up and
+    # drain gaps (slabs.py: SlabGroup): +4.5 % on a slab of the size one GPU gets at N = 8, nothing at N <= 2
+    # (profiles/r1/tuning_q.txt); not the default because it could not be measured on eight GPUs this round
+    sub = args.sub if args.sub > 0 else 1
+    if not (fused and args.halo == "p2p" and W % 16 == 0 and H // (world * sub) >= HALO_ROWS + 9):
+        sub = 1
+    if sub > 1:
+        r = SlabGroup(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, sub=sub)
+    else:
+        r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
     import cedecrt
-    r.rt.set_math_mode({"libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_FAST, "exact": cedecrt.MATH_EXACT}[args.math])
+    r.set_math_mode({"libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_FAST, "exact": cedecrt.MATH_EXACT}[args.math])
     stats = r.geom.stats()
-    if world > 1 and not args.no_balance:
+    if world * sub > 1 and not args.no_balance:
         r.calibrate(rounds=3, frames=4)  # static camera: balance the slab heights on throw-away frames before the sequence starts
 
     def barrier():
@@ -211,8 +224,8 @@ def run_cuda(args):
     for _ in range(args.warmup):
         r.frame()
     barrier()
-    launches0 = r.rt.launch_count()
-    rays0 = r.rt.shadow_rays_traced()
+    launches0 = r.launch_count()
+    rays0 = r.shadow_rays_traced()
     sampler.mark_begin()
     # ---- timed: K frames, resident buffers
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -220,11 +233,12 @@ def run_cuda(args):
     e0.record()
     for _ in range(args.steps):
         r.frame()
+    r.join()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = r.rt.launch_count() - launches0
-    rays1 = r.rt.shadow_rays_traced()
+    launches = r.launch_count() - launches0
+    rays1 = r.shadow_rays_traced()
     shadow_rays = [(b - a) / args.steps for a, b in zip(rays0, rays1)]  # per frame: (visibility reuse, resolve)
     # ---- timed: K frames end to end (per-frame D2H of the RGBA8 image into pinned host memory)
     if args.readback == "pipelined":
@@ -236,7 +250,8 @@ def run_cuda(args):
         for _ in range(args.steps):
             r.frame()
             r.download_pixels()
-            torch.cuda.current_stream().synchronize()  # oroStreamSynchronize after the copy (10_restir_di.cpp:389)
+            for sl in r.slabs:
+                sl.stream.synchronize()  # oroStreamSynchronize after the copy (10_restir_di.cpp:389)
     else:
         # pipelined: frame i's image travels on a copy stream while frame i+1 renders; the host takes delivery of
         # image i-1 (one frame of latency, as a display loop has); every frame's copy lies inside the timed region
@@ -248,7 +263,9 @@ def run_cuda(args):
                 r.wait_download(prev)
             prev = slot
         r.wait_download(prev)
-        torch.cuda.current_stream().wait_event(r._copy_events[prev])
+        for ev in r.last_copy_events(prev):
+            torch.cuda.current_stream().wait_event(ev)
+    r.join()
     t_e1.record()
     barrier()
     ms_e2e = t_e0.elapsed_time(t_e1)
@@ -270,7 +287,7 @@ def run_cuda(args):
     # inside the north star's tolerance of the oracle but not bit-comparable; include/cedecrt.h)
     ms_fast = None
     if fused and args.math == "libdevice" and not args.no_fast_line:
-        r.rt.set_math_mode(cedecrt.MATH_FAST)
+        r.set_math_mode(cedecrt.MATH_FAST)
         for _ in range(2):
             r.frame()
         barrier()
@@ -278,10 +295,11 @@ def run_cuda(args):
         f0.record()
         for _ in range(args.steps):
             r.frame()
+        r.join()
         f1.record()
         barrier()
         ms_fast = f0.elapsed_time(f1)
-        r.rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
+        r.set_math_mode(cedecrt.MATH_LIBDEVICE)
         r.frame()
     # ---- per-kernel device times: an event after every launch (crt_profile_begin/end), steady-state frames
     n_prof = max(2, min(args.steps, 4))
@@ -294,6 +312,7 @@ def run_cuda(args):
     per_kernel = {}
     for name, t_ms in marks:
         per_kernel.setdefault(name, []).append(t_ms)
+    r.check()  # a halo wait that timed out would have invalidated every number above
     n_px, n_diffuse = pixel_classes(torch, r)
     # rays actually traced per frame: 1 primary per pixel + the shadow rays counted by the tracer (the reference traces
     # 2 per diffuse pixel; the fused frame skips those whose answer it already holds, see include/cedecrt.h)
@@ -350,8 +369,8 @@ def run_cuda(args):
                        "mode": "fused frame (crt_restir_frame_begin / spatial_pass / frame_end, SoA reservoirs)" if fused
                                else "per-kernel launch list (drop-in, AoS reservoirs)",
                        "slab_edges": r.edges,
-                       "partition": "%d row slab(s), halo %d rows, %s" % (
-                           world, HALO_ROWS, "halo rows stored directly into the neighbours' buffers over NVLink "
+                       "partition": "%d row slab(s)%s, halo %d rows, %s" % (
+                           world * sub, " (%d per GPU, one CUDA stream each)" % sub if sub > 1 else "", HALO_ROWS, "halo rows stored directly into the neighbours' buffers over NVLink "
                            "(cudaIpc peer pointers, csrc/slab_p2p.cu)" if r.p2p else
                            "%d halo bytes sent per frame by rank 0 (NCCL send/recv)" % halo_bytes_per_frame),
                        "l2": "per-frame working set (3 x 600 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
@@ -526,6 +545,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=64, help="band height of the CPU arm's per-step sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-line", action="store_true", help="skip the additional CRT_MATH_FAST measurement")
+    ap.add_argument("--sub", type=int, default=0,
+                    help="row slabs (contexts + streams) per GPU (slabs.py: SlabGroup); default 1")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal-height slabs (no calibration frames)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1, fused mode: halo rows by direct peer stores (default) or NCCL send/recv")

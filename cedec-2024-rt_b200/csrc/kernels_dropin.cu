@@ -115,6 +115,16 @@ __global__ void __launch_bounds__(256)
     const TilePix t = this_pixel(W, H, rows);
     if (t.in) pixels[t.px.idx] = px_ao<Math<MODE>>(t.px, raygen, W, H, bvh, tris60, n_rays);
 }
+// the kernels of this file the fused frame launches (crt_slab_set_links loads them ahead of any spinning wait)
+int preload_dropin_kernels()
+{
+    cudaFuncAttributes a;
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_raycast));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_tone_mapping<0>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_tone_mapping<1>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_clear));
+    return CRT_OK;
+}
 }  // namespace crt
 
 // ======================================================================================= C ABI

@@ -108,11 +108,24 @@ void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H,
 {
     k_resolve_fast<<<grid, 256, 0, st>>>(accum, W, H, rows, tris60, vis, res, g, q, accumulate, reuse_traced);
 }
+int preload()
+{
+    cudaFuncAttributes a;
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_candidate_temporal<LightsTable, 0>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_candidate_temporal<LightsTable, 1>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_candidate_temporal<LightsIndexed, 0>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_candidate_temporal<LightsIndexed, 1>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_spatial_fast<0>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_spatial_fast<1>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_resolve_fast));
+    return CRT_OK;
+}
 }  // namespace CRT_KNS
 
 #if !defined(CRT_FASTMATH_TU)
 namespace fm
 {
+int preload();
 void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
                                const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
                                const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
@@ -131,6 +144,16 @@ __global__ void __launch_bounds__(256) k_clear_traced(size_t n, SoaStore s)
         const uint32_t v = *w;
         if (v & kTracedBit) *w = v & ~kTracedBit;
     }
+}
+int preload_fused_kernels()
+{
+    cudaFuncAttributes a;
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_clear_traced));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_trace_shadow_queue<kEpiSoaVisibility>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_trace_shadow_queue<kEpiResolve>));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_build_light_table));
+    const int rc = ex::preload();
+    return rc != CRT_OK ? rc : fm::preload();
 }
 // layout conversion for inspection / parity dumps / switching modes with history
 __global__ void __launch_bounds__(256) k_soa_to_aos(size_t n, SoaStore s, crt_reservoir* aos)

@@ -126,6 +126,13 @@ static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60,
 }
 }  // namespace crt
 
+namespace crt
+{
+// force the (lazily loaded) kernels of a translation unit into the context; see crt_slab_set_links
+int preload_fused_kernels();
+int preload_dropin_kernels();
+}  // namespace crt
+
 #define CRT_CHECK_IMAGE(W, H) CRT_REQUIRE((W) > 0 && (H) > 0 && (size_t)(W) * (size_t)(H) < 0x7fffffffull, "bad image size")
 #define CRT_CHECK_BUF(b, n, what) CRT_REQUIRE((b).data != nullptr && bsize(b) >= (size_t)(n), what " buffer too small or null")
 

@@ -31,17 +31,36 @@ __global__ void __launch_bounds__(256) k_push_halo(CopyPlan plan)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < s.n16; i += (size_t)gridDim.x * blockDim.x)
         s.dst[i] = __ldg(s.src + i);
 }
-// raise `value` in the neighbours' slots, then wait for them to raise mine
+// raise `value` in the neighbours' slots, then wait for them to raise mine.  A neighbour that has not answered after
+// kWaitLimitNs (a host that stopped issuing, a slab that failed) must not hang the GPU: the wait gives up and leaves
+// the stage number in mine[2], which crt_slab_status reports.
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __global__ void k_signal_wait(unsigned long long* up_slot, unsigned long long* down_slot, volatile unsigned long long* mine,
                               unsigned long long value)
 {
     __threadfence_system();
     if (up_slot) atomicExch_system(up_slot, value);
     if (down_slot) atomicExch_system(down_slot, value);
-    if (up_slot)
-        while (mine[0] < value) __nanosleep(200);
-    if (down_slot)
-        while (mine[1] < value) __nanosleep(200);
+    const unsigned long long t0 = global_ns();
+    for (int side = 0; side < 2; side++)
+    {
+        if (!(side ? down_slot : up_slot)) continue;
+        while (mine[side] < value)
+        {
+            __nanosleep(200);
+            if (global_ns() - t0 > kWaitLimitNs)
+            {
+                mine[2] = value;
+                break;
+            }
+        }
+    }
     __threadfence_system();
 }
 }  // namespace crt
@@ -100,9 +119,30 @@ extern "C" int crt_slab_set_links(crt_ctx* ctx, const crt_slab_links* links)
         return CRT_OK;
     }
     CRT_REQUIRE(links->my_flags != nullptr, "null flag buffer");
+    // With lazy module loading, the first launch of a kernel loads it, and loading waits for the device to go idle:
+    // a slab whose wait kernel is already spinning for a neighbour driven by this same host thread would never see
+    // that neighbour's launch.  Every kernel of the frame is therefore loaded now.
+    {
+        cudaFuncAttributes a;
+        CRT_CUDA(cudaFuncGetAttributes(&a, k_signal_wait));
+        CRT_CUDA(cudaFuncGetAttributes(&a, k_push_halo));
+        int rc = preload_fused_kernels();
+        if (rc == CRT_OK) rc = preload_dropin_kernels();
+        if (rc != CRT_OK) return rc;
+    }
     ctx->links = *links;
     ctx->links_set = true;
     ctx->link_epoch = 0;
+    return CRT_OK;
+}
+
+extern "C" int crt_slab_status(crt_ctx* ctx, unsigned long long* timed_out_stage)
+{
+    CRT_REQUIRE(ctx && timed_out_stage, "null argument");
+    *timed_out_stage = 0;
+    if (!ctx->links_set) return CRT_OK;
+    CRT_CUDA(cudaMemcpyAsync(timed_out_stage, (const char*)ctx->links.my_flags + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRT_OK;
 }
 

@@ -166,6 +166,7 @@ def _load():
         "crt_ipc_open": [P, C.c_char_p, C.POINTER(C.c_void_p)],
         "crt_ipc_close": [P, C.c_void_p],
         "crt_restir_reserve": [P, I, I, C.POINTER(C.c_void_p)],
+        "crt_slab_status": [P, C.POINTER(C.c_ulonglong)],
         "crt_slab_set_links": [P, C.POINTER(SlabLinks)],
         "crt_slab_exchange": [P, I, I, I, I, C.POINTER(RestirBuffers)],
         "crt_launch": [P, C.c_char_p, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
@@ -485,6 +486,12 @@ class Runtime:
 
     def slab_set_links(self, links):
         self._check(self.lib.crt_slab_set_links(self.ctx, C.byref(links) if links is not None else None))
+
+    def slab_status(self):
+        """0, or the exchange count at which a wait for a neighbouring slab timed out"""
+        out = C.c_ulonglong(0)
+        self._check(self.lib.crt_slab_status(self.ctx, C.byref(out)))
+        return int(out.value)
 
     def slab_exchange(self, W, H, which, bufs, push_rows=0):
         self._check(self.lib.crt_slab_exchange(self.ctx, W, H, which, push_rows, C.byref(bufs)))

@@ -130,9 +130,14 @@ class SlabRenderer:
     """The frame loop over one GPU's row slab.  Buffers are full-size (pixel indices stay global) and are torch
     tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
 
-    def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True, edges=None, options=None, p2p=True):
+    def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True, edges=None, options=None, p2p=True,
+                 stream=None, share=None, connect=True):
         """p2p: in fused mode with more than one rank, exchange halo rows by direct peer stores (csrc/slab_p2p.cu,
-        buffers shared through cudaIpc handles) instead of NCCL send/recv; needs slabs >= HALO rows, W % 16 == 0"""
+        buffers shared through cudaIpc handles) instead of NCCL send/recv; needs slabs >= HALO rows, W % 16 == 0.
+        stream: the torch stream this slab's kernels go to (default: the current one).  share: another SlabRenderer on
+        the same GPU whose scene, light list and BVH this one uses instead of uploading and building its own.
+        connect=False leaves the neighbour links to the caller (SlabGroup: slabs of one process are linked by plain
+        pointers, `rank`/`world` then count slabs, not processes)."""
         import numpy as np
 
         import cedecrt
@@ -140,8 +145,9 @@ class SlabRenderer:
         self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
         self.c, self.fused = cedecrt, fused
         self.rt = cedecrt.Runtime(torch.cuda.current_device())
-        assert torch.cuda.current_stream().cuda_stream != 0, "bench needs a non-default torch stream"
-        self.rt.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.stream = stream if stream is not None else torch.cuda.current_stream()
+        assert self.stream.cuda_stream != 0, "bench needs a non-default torch stream"
+        self.rt.set_stream(self.stream.cuda_stream)
         self.edges = edges if edges is not None else [slab_rows(H, world, r)[0] for r in range(world)] + [H]
         self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
         self.plan = halo_plan(H, self.edges, rank) if world > 1 else []
@@ -166,13 +172,19 @@ class SlabRenderer:
             t = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
             return t, self.rt.wrap(t.data_ptr(), dtype, count)
 
-        self.t_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).to(dev)
-        self.triangles = self.rt.wrap(self.t_tris.data_ptr(), cedecrt.TRIANGLE, len(tris))
-        lights = cedecrt.light_indices(tris)
-        self.t_lights = torch.from_numpy(lights.view(np.uint8)).to(dev)
-        self.lights = self.rt.wrap(self.t_lights.data_ptr(), np.uint32, len(lights))
-        self.n_tris, self.n_lights = len(tris), len(lights)
-        self.geom = self.rt.build_geometry(self.triangles)
+        if share is not None:
+            self.t_tris, self.t_lights, self.geom = share.t_tris, share.t_lights, share.geom
+            self.n_tris, self.n_lights = share.n_tris, share.n_lights
+            self.triangles = self.rt.wrap(self.t_tris.data_ptr(), cedecrt.TRIANGLE, self.n_tris)
+            self.lights = self.rt.wrap(self.t_lights.data_ptr(), np.uint32, self.n_lights)
+        else:
+            self.t_tris = torch.from_numpy(tris.view(np.uint8).reshape(-1)).to(dev)
+            self.triangles = self.rt.wrap(self.t_tris.data_ptr(), cedecrt.TRIANGLE, len(tris))
+            lights = cedecrt.light_indices(tris)
+            self.t_lights = torch.from_numpy(lights.view(np.uint8)).to(dev)
+            self.lights = self.rt.wrap(self.t_lights.data_ptr(), np.uint32, len(lights))
+            self.n_tris, self.n_lights = len(tris), len(lights)
+            self.geom = self.rt.build_geometry(self.triangles)
         self.t_pix, self.pixels = tbuf(4 * n, np.uint8, 4 * n)
         self.t_acc, self.accumulation = tbuf(16 * n, cedecrt.FLOAT4, n, zero=True)
         self.t_vis, self.visibility = tbuf(16 * n, cedecrt.VISIBILITY, n, zero=True)
@@ -191,36 +203,47 @@ class SlabRenderer:
         self._host_ring = None
         self._copies = 0
         self._copy_pending = None
-        if self.p2p:
-            self._connect_peers()
+        if self.p2p and connect:
+            everyone = [None] * self.world
+            self.dist.all_gather_object(everyone, self.export_links())
+            self.connect_links(everyone)
+            self.dist.barrier()  # nobody starts rendering before every rank has opened its neighbours' buffers
 
-    def _connect_peers(self):
-        """share the reservoir buffers, the pixel-class plane and a flag buffer with the adjacent ranks"""
+    _LINKED = ("temporal", "reservoir0", "reservoir1", "scratch", "flags")
+
+    def export_links(self):
+        """what a neighbouring slab needs to store into this one: cudaIpc handles of the three reservoir buffers, the
+        scratch allocation (pixel-class plane) and the flag buffer, plus the raw pointers for a neighbour that lives in
+        the same process"""
+        import os
+
+        rt = self.rt
+        scratch = rt.restir_reserve(self.W, self.H)
+        self._flags = rt.buffer("u1", 32).zero()  # two neighbour slots + the wait kernel's time-out mark
+        rt.sync()
+        ptrs = {"temporal": self.temporal.ptr, "reservoir0": self.reservoir0.ptr, "reservoir1": self.reservoir1.ptr,
+                "scratch": scratch, "flags": self._flags.ptr}
+        return {"pid": os.getpid(), "ptr": ptrs, "ipc": {k: rt.ipc_export(v) for k, v in ptrs.items()}}
+
+    def connect_links(self, everyone):
+        """everyone[slab] = that slab's export_links(); opens the adjacent slabs' buffers and registers them"""
         import ctypes as C
+        import os
 
         rt, n = self.rt, self.W * self.H
-        scratch = rt.restir_reserve(self.W, self.H)
-        self._flags = rt.buffer("u1", 16).zero()
-        rt.sync()
-        mine = {"temporal": rt.ipc_export(self.temporal.ptr), "reservoir0": rt.ipc_export(self.reservoir0.ptr),
-                "reservoir1": rt.ipc_export(self.reservoir1.ptr), "scratch": rt.ipc_export(scratch),
-                "flags": rt.ipc_export(self._flags.ptr)}
-        everyone = [None] * self.world
-        self.dist.all_gather_object(everyone, mine)
         links = self.c.SlabLinks()
         links.my_flags = self._flags.ptr
         for side, peer in (("up", self.rank - 1), ("down", self.rank + 1)):
             if peer < 0 or peer >= self.world:
                 continue
             h = everyone[peer]
-            ptrs = [rt.ipc_open(h[k]) for k in ("temporal", "reservoir0", "reservoir1")]
-            ptrs.append(rt.ipc_open(h["scratch"]) + 24 * n)
-            flags = rt.ipc_open(h["flags"])
+            local = h["pid"] == os.getpid()  # a handle cannot be opened by the process that exported it
+            at = {k: (h["ptr"][k] if local else rt.ipc_open(h["ipc"][k])) for k in self._LINKED}
+            ptrs = [at["temporal"], at["reservoir0"], at["reservoir1"], at["scratch"] + 24 * n]
             getattr(links, side)[:] = (C.c_void_p * 4)(*ptrs)
             # I am the peer's "down" neighbour if it is above me, so I raise its slot 1; and vice versa
-            setattr(links, side + "_flag", flags + (8 if side == "up" else 0))
+            setattr(links, side + "_flag", at["flags"] + (8 if side == "up" else 0))
         rt.slab_set_links(links)
-        self.dist.barrier()  # nobody starts rendering before every rank has opened its neighbours' buffers
 
     def set_edges(self, edges):
         """move the slab boundaries (before any frame whose history matters: see calibrate)"""
@@ -231,9 +254,33 @@ class SlabRenderer:
         self.host_pixels = self.torch.empty(4 * self.W * max(self.y1 - self.y0, 1), dtype=self.torch.uint8).pin_memory()
 
     def reset_history(self):
-        for t in (self.t_tmp, self.t_r0, self.t_r1, self.t_acc):
-            t.zero_()
+        with self.torch.cuda.stream(self.stream):
+            for t in (self.t_tmp, self.t_r0, self.t_r1, self.t_acc):
+                t.zero_()
         self.frame_index = 0
+
+    # -- the interface bench.py uses on a SlabRenderer and on a SlabGroup alike
+    slabs = property(lambda self: [self])
+
+    def join(self):
+        pass
+
+    def check(self):
+        stage = self.rt.slab_status() if self.p2p else 0
+        if stage:
+            raise RuntimeError("slab %d: wait for a neighbour timed out at exchange %d" % (self.rank, stage))
+
+    def launch_count(self):
+        return self.rt.launch_count()
+
+    def shadow_rays_traced(self):
+        return self.rt.shadow_rays_traced()
+
+    def set_math_mode(self, mode):
+        self.rt.set_math_mode(mode)
+
+    def last_copy_events(self, slot):
+        return [self._copy_events[slot]]
 
     def calibrate(self, rounds=2, frames=2):
         """Load balancing for a static camera: render a few throw-away frames, measure every slab's own kernel time
@@ -269,16 +316,12 @@ class SlabRenderer:
 
     def frame(self):
         rt, W, H, o, g, t, v, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.visibility, self.eye
+        if self.fused and self.p2p:
+            for stage in range(self.n_stages()):
+                self.frame_stage(stage)
+            return
         self.frame_index += 1
         f = self.frame_index
-        if self.fused and self.p2p:
-            rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
-            for k in range(o.spatial_resampling_passes):  # input of pass k: temporal, reservoir1, reservoir0, ...
-                rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), self.bufs)  # rows were mirrored by the kernels
-                rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
-            self._before_pixels_rewrite()
-            rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
-            return
         if self.fused:
             rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
             for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
@@ -303,10 +346,31 @@ class SlabRenderer:
         self._before_pixels_rewrite()
         rt.tone_mapping(self.pixels, self.accumulation, W, H)
 
+    def n_stages(self):
+        return 2 + self.options.spatial_resampling_passes
+
+    def frame_stage(self, stage):
+        """the fused frame with direct halo stores, one stage per call (0: raycast + candidates + temporal; 1..passes:
+        wait for the neighbours' halo rows, then one spatial pass; last: resolve + tone mapping) so that a SlabGroup can
+        issue the stages of its slabs alternately"""
+        rt, W, H, o, g, t, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.eye
+        passes = o.spatial_resampling_passes
+        if stage == 0:
+            self.frame_index += 1
+            rt.restir_frame_begin(W, H, self.frame_index, g, t, self.raygen, eye, self.lights, o, self.bufs)
+        elif stage <= passes:
+            k = stage - 1  # input of pass k: temporal, reservoir1, reservoir0, ...
+            rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), self.bufs)  # rows were mirrored by the kernels
+            rt.restir_spatial_pass(W, H, self.frame_index, k, g, t, eye, o, self.bufs)
+        else:
+            self._before_pixels_rewrite()
+            rt.restir_frame_end(W, H, g, t, eye, o, self.bufs)
+
     def download_pixels(self):
         """the reference's read-back (10_restir_di.cpp:386-389): copy on the frame's own stream; the caller synchronises"""
         src = self._rows(self.t_pix, 4, self.y0, self.y1)
-        self.host_pixels.copy_(src, non_blocking=True)
+        with self.torch.cuda.stream(self.stream):
+            self.host_pixels.copy_(src, non_blocking=True)
 
     def download_pixels_async(self):
         """Pipelined read-back: this frame's RGBA8 rows travel to pinned host memory on a copy stream while the next
@@ -321,7 +385,7 @@ class SlabRenderer:
         slot = self._copies % 2
         self._copies += 1
         rendered = torch.cuda.Event()
-        rendered.record()  # on the frame's stream
+        rendered.record(self.stream)
         self._copy_stream.wait_event(rendered)
         src = self._rows(self.t_pix, 4, self.y0, self.y1)
         with torch.cuda.stream(self._copy_stream):
@@ -339,5 +403,163 @@ class SlabRenderer:
 
     def _before_pixels_rewrite(self):
         if self._copy_pending is not None:
-            self.torch.cuda.current_stream().wait_event(self._copy_pending)
+            self.stream.wait_event(self._copy_pending)
             self._copy_pending = None
+
+
+class SlabGroup:
+    """Several row slabs per GPU, each with its own context and CUDA stream, driven by one process.
+
+    A slab's kernels at 4 or 8 GPUs last tens to hundreds of microseconds: ten dependent launches per frame, each with
+    its ramp-up and — the persistent ray tracers above all — its drain, during which most of the GPU idles.  Two
+    independent kernel sequences on two streams fill each other's gaps: measured on one B200 with two slab-sized frames,
+    1.29 x the throughput of one stream at 272 rows, 1.12 x at 544, 1.03 x at 2160 (profiles/overlap_probe.py).  So every
+    rank renders `sub` slabs instead of one.  Slabs of one process are linked by plain device pointers, slabs of
+    different processes through cudaIpc as before; scene, light list and BVH are shared by the slabs of a GPU.  The
+    image is the same bit for bit (tests/gpu_slab_worker.py).
+
+    The interface is the part of SlabRenderer's that bench.py and the tests use."""
+
+    def __init__(self, torch, dist, rank, world, tris, cam, W, H, sub=2, options=None):
+        self.torch, self.dist, self.rank, self.world, self.W, self.H, self.sub = torch, dist, rank, world, W, H, sub
+        vworld = world * sub
+        edges = [slab_rows(H, vworld, r)[0] for r in range(vworld)] + [H]
+        self.stream = torch.cuda.current_stream()
+        self.streams = [self.stream] + [torch.cuda.Stream() for _ in range(sub - 1)]
+        self.slabs = []
+        for j, st in enumerate(self.streams):
+            with torch.cuda.stream(st):
+                self.slabs.append(SlabRenderer(torch, dist, rank * sub + j, vworld, tris, cam, W, H, fused=True,
+                                               edges=edges, options=options, p2p=True, stream=st,
+                                               share=self.slabs[0] if j else None, connect=False))
+        assert all(s.p2p for s in self.slabs), "slabs too thin for direct halo stores (needs >= %d rows each)" % HALO
+        # One whole frame of the first slab alone, in both arithmetic modes, before any slab can wait for another: it
+        # builds the shared geometry's light records and has every kernel of the frame loaded (with lazy module loading
+        # a first launch waits for the device to go idle, which it never would under a spinning wait kernel).
+        first = self.slabs[0]
+        for mode in (first.c.MATH_FAST, first.c.MATH_LIBDEVICE):
+            first.rt.set_math_mode(mode)
+            first.rt.restir_di_frame(W, H, 1, first.geom, first.triangles, first.raygen, first.eye, first.lights,
+                                     first.options, first.bufs)
+        torch.cuda.synchronize()
+        mine = [s.export_links() for s in self.slabs]
+        everyone = [mine]
+        if world > 1:
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+        flat = [h for per_rank in everyone for h in per_rank]
+        for s in self.slabs:
+            s.connect_links(flat)
+        self._barrier()
+        self.reset_history()
+        self._barrier()
+        first = self.slabs[0]
+        self.rt, self.geom, self.n_tris, self.n_lights, self.p2p = first.rt, first.geom, first.n_tris, first.n_lights, True
+        self.halo_bytes = 0
+
+    # -- plumbing
+    def _barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    @property
+    def edges(self):
+        return self.slabs[0].edges
+
+    @property
+    def y0(self):
+        return self.slabs[0].y0
+
+    @property
+    def y1(self):
+        return self.slabs[-1].y1
+
+    def check(self):
+        """raise if a slab's wait for a neighbour timed out (csrc/slab_p2p.cu: k_signal_wait)"""
+        for s in self.slabs:
+            stage = s.rt.slab_status()
+            if stage:
+                raise RuntimeError("slab %d: wait for a neighbour timed out at exchange %d" % (s.rank, stage))
+
+    def join(self):
+        """the group's first stream (the one callers time and synchronise) waits for the other slabs' streams"""
+        for st in self.streams[1:]:
+            ev = self.torch.cuda.Event()
+            ev.record(st)
+            self.stream.wait_event(ev)
+
+    def fork(self):
+        """the other slabs' streams wait for what has been issued to the first one"""
+        ev = self.torch.cuda.Event()
+        ev.record(self.stream)
+        for st in self.streams[1:]:
+            st.wait_event(ev)
+
+    def frame(self):
+        # stage by stage over the slabs, so that every stream always has the next kernel queued
+        for stage in range(self.slabs[0].n_stages()):
+            for s in self.slabs:
+                s.frame_stage(stage)
+
+    def reset_history(self):
+        for s in self.slabs:
+            s.reset_history()
+
+    def set_edges(self, edges):
+        for s in self.slabs:
+            s.set_edges(edges)
+
+    def calibrate(self, rounds=3, frames=4):
+        """as SlabRenderer.calibrate, over all slabs of all ranks; a slab's time is measured while the GPU is shared with
+        the rank's other slabs, which is the condition it will run under"""
+        torch = self.torch
+        vworld = self.world * self.sub
+        for _ in range(rounds):
+            self._barrier()
+            self.reset_history()
+            self._barrier()
+            self.frame()
+            for s in self.slabs:
+                s.rt.profile_begin()
+            for _ in range(frames):
+                self.frame()
+            t = torch.zeros(vworld, dtype=torch.float64, device="cuda")
+            for s in self.slabs:
+                marks = s.rt.profile_end()
+                t[s.rank] = sum(ms for name, ms in marks if name != "signal_wait") / frames
+            if self.world > 1:
+                self.dist.all_reduce(t)
+            self.set_edges(rebalance(self.edges, [float(x) for x in t.tolist()], 8, HALO + 9))
+        self._barrier()
+        self.reset_history()
+        self._barrier()
+        return self.edges
+
+    # -- what bench.py reads
+    def launch_count(self):
+        return sum(s.rt.launch_count() for s in self.slabs)
+
+    def shadow_rays_traced(self):
+        a = [s.rt.shadow_rays_traced() for s in self.slabs]
+        return sum(x[0] for x in a), sum(x[1] for x in a)
+
+    def set_math_mode(self, mode):
+        for s in self.slabs:
+            s.rt.set_math_mode(mode)
+
+    def download_pixels(self):
+        for s in self.slabs:
+            s.download_pixels()
+
+    def download_pixels_async(self):
+        return [s.download_pixels_async() for s in self.slabs]
+
+    def wait_download(self, slots):
+        return [s.wait_download(k) for s, k in zip(self.slabs, slots)]
+
+    def last_copy_events(self, slots):
+        return [s._copy_events[k] for s, k in zip(self.slabs, slots)]
+
+    def _rows(self, t, elem, a, b):
+        return self.slabs[0]._rows(t, elem, a, b)

@@ -266,6 +266,9 @@ int crt_slab_set_links(crt_ctx* ctx, const crt_slab_links* links);
  * mirror their boundary rows into the neighbours' buffers, so push_rows = 0 only signals the neighbours and waits
  * for theirs; push_rows = 1 first copies the 87 boundary rows of the buffer with a dedicated kernel, 2 also the
  * pixel-class rows (for buffers filled by other means). */
+/* 0, or the exchange count at which a wait for a neighbour gave up after 4 s (the frame is then invalid); waits for the
+ * stream.  The flag buffer registered with crt_slab_set_links is 32 bytes: two slots and this mark. */
+int crt_slab_status(crt_ctx* ctx, unsigned long long* timed_out_stage);
 int crt_slab_exchange(crt_ctx* ctx, int width, int height, int which, int push_rows,
                       const crt_restir_buffers* buffers);
 

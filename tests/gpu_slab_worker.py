@@ -22,26 +22,33 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream())
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    mode = os.environ.get("SLAB_MODE", "fused")  # fused (direct peer stores) | fused_nccl | dropin (NCCL)
+    mode = os.environ.get("SLAB_MODE", "fused")  # fused (direct peer stores) | fused_nccl | dropin (NCCL) | group
     fused = mode != "dropin"
     if stage_assets.have_scene("blocks_restir"):
         tris = stage_assets.load_scene("blocks_restir")
         cam, W, H = ((-0.579885, 22.194597, -6.567105), (5.224952, 20.847435, 1.431192)), 960, 540
+        if mode == "group":
+            H = 1080  # two slabs per GPU, each at least a halo tall
     else:
         tris = small_scene("blocks_ao").copy()
         tris["emissive"][100:140] = (5.0, 4.0, 3.0)
         cam, W, H = ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0)), 320, 400
-    part = slabs.SlabRenderer(torch, dist, rank, world, tris, cam, W, H, fused=fused, p2p=(mode == "fused"))
+    if mode == "group":  # two slabs per GPU on two streams (slabs.SlabGroup), linked by pointers within a process
+        part = slabs.SlabGroup(torch, dist, rank, world, tris, cam, W, H, sub=2)
+        part.calibrate(rounds=1, frames=1)  # uneven slabs, and a history reset in between
+    else:
+        part = slabs.SlabRenderer(torch, dist, rank, world, tris, cam, W, H, fused=fused, p2p=(mode == "fused"))
     full = slabs.SlabRenderer(torch, None, 0, 1, tris, cam, W, H, fused=fused)
     for _ in range(3):
         part.frame()
         full.frame()
     torch.cuda.synchronize()
     ok = True
-    for name, elem in (("t_acc", 16), ("t_pix", 4), ("t_vis", 16)):
-        a = part._rows(getattr(part, name), elem, part.y0, part.y1)
-        b = full._rows(getattr(full, name), elem, part.y0, part.y1)
-        ok = ok and bool(torch.equal(a, b))
+    for sl in part.slabs:
+        for name, elem in (("t_acc", 16), ("t_pix", 4), ("t_vis", 16)):
+            a = sl._rows(getattr(sl, name), elem, sl.y0, sl.y1)
+            b = full._rows(getattr(full, name), elem, sl.y0, sl.y1)
+            ok = ok and bool(torch.equal(a, b))
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:

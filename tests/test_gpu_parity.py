@@ -635,7 +635,33 @@ def test_reservoir_layout_round_trip(rt):
     assert reservoir_mismatch(a, d_b.to_host()) == 0
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_nccl", "dropin"])
+def test_slab_group_on_one_gpu():
+    """three row slabs on one GPU, each with its own context and stream, halo rows stored through plain pointers
+    (slabs.SlabGroup, what bench.py uses per rank at N > 1): the frame equals the single-slab frame bit for bit"""
+    import torch
+
+    import slabs
+
+    tris = staged("blocks_restir")
+    W, H = 960, 540
+    torch.cuda.set_device(0)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        part = slabs.SlabGroup(torch, None, 0, 1, tris, CAM_RESTIR, W, H, sub=3)
+        part.calibrate(rounds=1, frames=1)
+        full = slabs.SlabRenderer(torch, None, 0, 1, tris, CAM_RESTIR, W, H, fused=True)
+        for _ in range(4):
+            part.frame()
+            full.frame()
+        torch.cuda.synchronize()
+        assert len(set(part.edges)) == 4 and part.edges[0] == 0 and part.edges[-1] == H
+        for sl in part.slabs:
+            for name, elem in (("t_acc", 16), ("t_pix", 4), ("t_vis", 16)):
+                a = sl._rows(getattr(sl, name), elem, sl.y0, sl.y1)
+                b = full._rows(getattr(full, name), elem, sl.y0, sl.y1)
+                assert torch.equal(a, b), (name, sl.rank)
+
+
+@pytest.mark.parametrize("mode", ["fused", "fused_nccl", "dropin", "group"])
 def test_slabs_on_gpus(mode):
     """N row slabs on N GPUs with NCCL halo exchange reproduce the single-GPU frame bit for bit (needs >= 2 GPUs)"""
     import subprocess
