@@ -197,15 +197,34 @@ def run_cuda(args):
     tris, cam, workload = load_workload()
     W, H = args.width, args.height
     fused = args.mode == "fused"
-    # slabs per GPU: 1 by default.  --sub 2 gives every rank two slabs on two streams that fill each other's ramp-up and
-    # drain gaps (slabs.py: SlabGroup): +4.5 % on a slab of the size one GPU gets at N = 8, nothing at N <= 2
-    # (profiles/r1/tuning_q.txt); not the default because it could not be measured on eight GPUs this round
-    sub = args.sub if args.sub > 0 else 1
+    # slabs per GPU (--sub; slabs.py: SlabGroup): two slabs on two streams fill each other's ramp-up and drain gaps.
+    # Measured on two GPUs with 272 rows each — one GPU's share of a 4K frame at N = 8 — 1342 against 1251 Mpix/s
+    # (+7 %), and nothing at N = 2 at 4K where the slabs are long enough (profiles/r1/tuning_q.txt).  So by default
+    # two slabs per GPU when a GPU's share is below 300 rows, one otherwise.
+    sub = args.sub if args.sub > 0 else (2 if world > 1 and H // world < 300 else 1)
     if not (fused and args.halo == "p2p" and W % 16 == 0 and H // (world * sub) >= HALO_ROWS + 9):
         sub = 1
+    r = None
     if sub > 1:
         r = SlabGroup(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, sub=sub)
-    else:
+        # pre-flight: two frames; if any slab's wait for a neighbour timed out anywhere, every rank falls back to one slab
+        for _ in range(2):
+            r.frame()
+        torch.cuda.synchronize()
+        bad = torch.tensor([0.0], device="cuda")
+        try:
+            r.check()
+        except RuntimeError as e:
+            print("bench.py: %s" % e, file=sys.stderr)
+            bad += 1
+        if world > 1:
+            dist.all_reduce(bad)
+        if bad.item() > 0:
+            r, sub = None, 1
+        else:
+            r.reset_history()
+            torch.cuda.synchronize()
+    if r is None:
         r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
     import cedecrt
     r.set_math_mode({"libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_FAST, "exact": cedecrt.MATH_EXACT}[args.math])
