@@ -331,7 +331,12 @@ def run_cuda(args):
     per_kernel = {}
     for name, t_ms in marks:
         per_kernel.setdefault(name, []).append(t_ms)
-    r.check()  # a halo wait that timed out would have invalidated every number above
+    timed_out = 0.0  # a halo wait that gave up (k_signal_wait's watchdog) invalidates every number of this run
+    try:
+        r.check()
+    except RuntimeError as e:
+        print("bench.py: %s" % e, file=sys.stderr)
+        timed_out = 1.0
     n_px, n_diffuse = pixel_classes(torch, r)
     # rays actually traced per frame: 1 primary per pixel + the shadow rays counted by the tracer (the reference traces
     # 2 per diffuse pixel; the fused frame skips those whose answer it already holds, see include/cedecrt.h)
@@ -343,7 +348,7 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(slab_ms)
     t = torch.tensor([ms, ms_e2e, float(rays), float(shadow_rays[0]), float(shadow_rays[1]), float(n_px), float(n_diffuse),
-                      float(ms_fast or 0.0)], dtype=torch.float64, device="cuda")
+                      float(ms_fast or 0.0), timed_out], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -353,6 +358,7 @@ def run_cuda(args):
         ms_fast = tmax[7].item() if ms_fast is not None else None
     rays_vr, rays_rs, all_px, all_diffuse = (t[3].item(), t[4].item(), t[5].item(), t[6].item()) if world == 1 else \
         (tsum[3].item(), tsum[4].item(), tsum[5].item(), tsum[6].item())
+    any_timed_out = (t[8].item() if world == 1 else tsum[8].item()) > 0
     if rank == 0:
         n_img = W * H
         peak, peak_src = measured_peaks()
@@ -420,6 +426,7 @@ def run_cuda(args):
                         "oracle after 64 frames 6e-5 (tolerance 1e-3; profiles/r1/long_horizon_parity.txt, "
                         "tests/test_gpu_parity.py::test_fast_math_mode_within_tolerance_over_64_frames). Not the headline."},
             "gpu_launches": int(launches),
+            "halo_wait_timed_out": bool(any_timed_out),  # true = a slab gave up waiting for a neighbour: the run is invalid
             "clocks": clocks,
             "roofline": {"kernel": dominant, "bound": "hbm",
                          "achieved": dom.get("algo_gbs"), "peak": peak, "unit": "GB/s",
