@@ -35,6 +35,7 @@ struct crt_ctx
     // slab_p2p.cu: peer pointers of the neighbouring slabs and the exchange counter
     crt_slab_links links = {};
     bool links_set = false;
+    bool frame_fused = true;  // the last crt_restir_frame_begin ran the fused bodies (SoA reservoirs), not the per-kernel path
     unsigned long long link_epoch = 0;
     int row_begin = 0, row_end = -1;  // rows of yi this context computes (crt_set_row_range); -1 = image height
     unsigned long long launches = 0;  // kernels launched through this context (bench.py: gpu_launches)

@@ -136,10 +136,14 @@ void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H,
                     const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q, int accumulate, int reuse_traced);
 }  // namespace fm
 // the traced marks of a history buffer stop being true when the geometry they were traced against is replaced
-__global__ void __launch_bounds__(256) k_clear_traced(size_t n, SoaStore s)
+// Only this context's own rows (pixels [first, first + n) of the bottom-up buffer): with slab links set, the halo rows
+// of the buffer are stored into by the neighbours' kernels — and rewritten by them in full every frame, marks included —
+// so a read-modify-write from here would race with those stores for nothing.
+__global__ void __launch_bounds__(256) k_clear_traced(size_t first, size_t n, SoaStore s)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
     {
+        const size_t i = first + k;
         uint32_t* w = s.mword((int)i);
         const uint32_t v = *w;
         if (v & kTracedBit) *w = v & ~kTracedBit;
@@ -273,6 +277,16 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     if (rc != CRT_OK) return rc;
     rc = crt_raycast(ctx, W, H, geom, triangles, raygen, b->visibility);
     if (rc != CRT_OK) return rc;
+    ctx->frame_fused = fused(options);
+    if (ctx->links_set)
+    {
+        // what the direct-store halo protocol (slab_p2p.cu) covers; anything else must use a host-side exchange
+        CRT_REQUIRE(ctx->frame_fused, "slab links are set but these options take the per-kernel path: exchange AoS rows on the host");
+        CRT_REQUIRE(!options.use_spatial_resampling || halo_rows_for(options.spatial_resampling_radius) <= kHaloRows,
+                    "slab links mirror 87 halo rows: spatial_resampling_radius above 30 needs a host-side exchange");
+        CRT_REQUIRE(!options.use_spatial_resampling || options.spatial_resampling_passes != 1,
+                    "slab links need 0 or >= 2 spatial passes (one signal/wait per pass orders the neighbours)");
+    }
     if (!fused(options))
     {
         rc = crt_generate_candidate(ctx, W, H, frame, geom, triangles, b->visibility, eye, lights, options, b->reservoir0);
@@ -299,7 +313,8 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     if (geom->serial != ctx->history_serial || b->temporal.data != ctx->history_buffer)
     {
         // another geometry (or another history buffer) than last frame's: its traced marks are not ours to trust
-        k_clear_traced<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, T);
+        const size_t own_first = (size_t)(H - rows.y1) * W, own_n = (size_t)(rows.y1 - rows.y0) * W;
+        if (own_n) k_clear_traced<<<sweep_blocks(ctx, own_n), 256, 0, ctx->stream>>>(own_first, own_n, T);
         rc = check_launch(ctx, "clear_traced");
         if (rc != CRT_OK) return rc;
         ctx->history_serial = geom->serial;

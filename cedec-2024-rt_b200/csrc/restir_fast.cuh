@@ -70,7 +70,14 @@ CRT_HD void store_u2(void* p, u2 v)
 // merges.  resolve uses it: when the final sample's origin is bit for bit this pixel's surface, the shadow ray of
 // 10_restir_di.cu:443-444 is the ray already traced, and its stored answer is used instead of tracing it again.
 constexpr int kSoaPlanes = 3;
-constexpr int kHaloRows = 87;  // rows a spatial pass can reach beyond a slab: |offset| <= 86.4 px (10_restir_di.cu:309-313)
+constexpr int kHaloRows = 87;  // rows a spatial pass can reach beyond a slab at the reference's radius 30: |offset| <= 86.4 px (10_restir_di.cu:309-313)
+// the same bound for any radius: offset = radius / 1.96 * sqrt(-2 ln rv0) * cos|sin, rv0 >= 2^-23, truncated towards
+// zero — which rounds the reach up on the side of smaller coordinates: floor(offset) + 1 rows; the factor covers the
+// float rounding of the product (python/slabs.py: halo_rows is the same formula)
+inline int halo_rows_for(float radius)
+{
+    return (int)floor(fabs((double)radius) / 1.96 * sqrt(-2.0 * log(ldexp(1.0, -23))) * (1.0 + 1e-5)) + 1;
+}
 CRT_HD size_t soa_plane_offset(int plane, size_t n) { return (size_t)plane * 32u * n; }
 CRT_HD size_t soa_plane_elem(int plane) { return plane < 2 ? 32u : 8u; }
 constexpr uint32_t kVisBit = 0x80000000u, kTracedBit = 0x40000000u, kSkipBit = 0x20000000u, kMMask = 0x1fffffffu;

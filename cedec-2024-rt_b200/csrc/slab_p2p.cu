@@ -152,6 +152,7 @@ extern "C" int crt_slab_exchange(crt_ctx* ctx, int W, int H, int which, int push
     CRT_REQUIRE(ctx && b, "null argument");
     CRT_REQUIRE(ctx->links_set, "crt_slab_set_links has not been called");
     CRT_REQUIRE(which >= 0 && which < 3, "which: 0 temporal, 1 reservoir0, 2 reservoir1");
+    CRT_REQUIRE(ctx->frame_fused, "the frame in flight took the per-kernel path (AoS reservoirs): exchange its rows on the host");
     CRT_CHECK_IMAGE(W, H);
     CRT_REQUIRE(W % 16 == 0, "direct halo stores need an image width that is a multiple of 16");
     const Rows rows = rows_of(ctx, H);

@@ -479,6 +479,9 @@ class Runtime:
         self._check(self.lib.crt_ipc_open(self.ctx, handle, C.byref(p)))
         return p.value
 
+    def ipc_close(self, ptr):
+        self._check(self.lib.crt_ipc_close(self.ctx, ptr))
+
     def restir_reserve(self, W, H):
         p = C.c_void_p()
         self._check(self.lib.crt_restir_reserve(self.ctx, W, H, C.byref(p)))

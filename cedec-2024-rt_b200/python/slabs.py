@@ -15,7 +15,17 @@ Nothing here touches pixel data itself: the functions compute byte ranges of bot
 code runs over NCCL on GPU tensors (bench.py) and over gloo on CPU tensors (tests/test_slabs.py).
 """
 
-HALO = 87  # rows; |neighbour offset| <= 86.4 px
+import math
+
+HALO = 87  # rows the direct-store (p2p) path mirrors: |neighbour offset| <= 86.4 px at the reference's radius 30 (csrc: kHaloRows)
+
+
+def halo_rows(radius):
+    """rows a spatial pass can reach beyond its own: the neighbour offset is radius / 1.96 * r * cos|sin(phi) with
+    r = sqrt(-2 ln rv0) and rv0 >= 2^-23 (rv0 = 0 gives an infinite offset, which is skipped as off-screen), truncated
+    towards zero (10_restir_di.cu:309-313, reservoir.hpp:89-95) — which rounds the reach *up* on the side of smaller
+    coordinates: floor(offset) + 1 rows; the factor covers the float rounding of the product"""
+    return int(math.floor(abs(float(radius)) / 1.96 * math.sqrt(-2.0 * math.log(2.0 ** -23)) * (1.0 + 1e-5))) + 1
 
 
 def slab_rows(H, world, rank, align=8):
@@ -143,23 +153,35 @@ class SlabRenderer:
         import cedecrt
 
         self.torch, self.dist, self.rank, self.world, self.W, self.H = torch, dist, rank, world, W, H
-        self.c, self.fused = cedecrt, fused
+        self.c = cedecrt
+        self.options = options or cedecrt.Options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+        # options the fused bodies do not cover (use_shadowed_target_function, an M bound past 2^29) make the crt_restir_*
+        # calls take the per-kernel path on AoS buffers (kernels_fast.cu: fused()): the host must then exchange AoS
+        # reservoir rows and Visibility rows, exactly as in drop-in mode
+        self.fused = bool(fused and cedecrt.lib().crt_restir_is_fused(self.options))
+        fused = self.fused
+        self.halo = halo_rows(self.options.spatial_resampling_radius) if self.options.use_spatial_resampling else 0
         self.rt = cedecrt.Runtime(torch.cuda.current_device())
         self.stream = stream if stream is not None else torch.cuda.current_stream()
         assert self.stream.cuda_stream != 0, "bench needs a non-default torch stream"
         self.rt.set_stream(self.stream.cuda_stream)
         self.edges = edges if edges is not None else [slab_rows(H, world, r)[0] for r in range(world)] + [H]
         self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
-        self.plan = halo_plan(H, self.edges, rank) if world > 1 else []
+        self.plan = halo_plan(H, self.edges, rank, self.halo) if world > 1 else []
         self.rt.set_row_range(self.y0, self.y1)
-        self.options = options or cedecrt.Options(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
         self.eye = tuple(float(np.float32(v)) for v in cam[0])
         self.raygen = cedecrt.lookat(cam[0], cam[1], W, H)
         n = W * H
         dev = torch.device("cuda", torch.cuda.current_device())
 
         heights = [b - a for a, b in zip(self.edges, self.edges[1:])]
-        self.p2p = bool(p2p and fused and world > 1 and W % 16 == 0 and min(heights) >= HALO)
+        # Direct peer stores need (a) slabs at least as tall as the mirrored band and a reach inside it (radius <= 30),
+        # (b) at least two spatial passes: the only ordering between neighbours is one signal/wait per pass
+        # (slab_p2p.cu), and with a single pass a fast neighbour could store frame f+1's temporal rows into this slab
+        # while its pass of frame f still reads them.  Otherwise the rows travel by NCCL send/recv.
+        passes_ok = (not self.options.use_spatial_resampling) or self.options.spatial_resampling_passes >= 2
+        self.p2p = bool(p2p and fused and world > 1 and W % 16 == 0 and min(heights) >= HALO and self.halo <= HALO
+                        and passes_ok)
         self._owned = []
 
         def tbuf(nbytes, dtype, count, zero=False, shared=False):
@@ -233,23 +255,39 @@ class SlabRenderer:
         rt, n = self.rt, self.W * self.H
         links = self.c.SlabLinks()
         links.my_flags = self._flags.ptr
+        self._opened = []
         for side, peer in (("up", self.rank - 1), ("down", self.rank + 1)):
             if peer < 0 or peer >= self.world:
                 continue
             h = everyone[peer]
             local = h["pid"] == os.getpid()  # a handle cannot be opened by the process that exported it
             at = {k: (h["ptr"][k] if local else rt.ipc_open(h["ipc"][k])) for k in self._LINKED}
+            if not local:
+                self._opened += list(at.values())
             ptrs = [at["temporal"], at["reservoir0"], at["reservoir1"], at["scratch"] + 24 * n]
             getattr(links, side)[:] = (C.c_void_p * 4)(*ptrs)
             # I am the peer's "down" neighbour if it is above me, so I raise its slot 1; and vice versa
             setattr(links, side + "_flag", at["flags"] + (8 if side == "up" else 0))
         rt.slab_set_links(links)
+        self._linked = True
+
+    def close(self):
+        """unlink from the neighbours and unmap their buffers (crt_ipc_close) before this slab's own buffers can go:
+        a peer that still had them mapped would otherwise keep storing into freed memory.  Collective in spirit —
+        every rank closes before any rank frees (callers put a barrier between close() and dropping the object)."""
+        if getattr(self, "_linked", False):
+            self.rt.sync()
+            self.rt.slab_set_links(None)
+            for p in self._opened:
+                self.rt.ipc_close(p)
+            self._opened = []
+            self._linked = False
 
     def set_edges(self, edges):
         """move the slab boundaries (before any frame whose history matters: see calibrate)"""
         self.edges = list(edges)
         self.y0, self.y1 = self.edges[self.rank], self.edges[self.rank + 1]
-        self.plan = halo_plan(self.H, self.edges, self.rank) if self.world > 1 else []
+        self.plan = halo_plan(self.H, self.edges, self.rank, self.halo) if self.world > 1 else []
         self.rt.set_row_range(self.y0, self.y1)
         self.host_pixels = self.torch.empty(4 * self.W * max(self.y1 - self.y0, 1), dtype=self.torch.uint8).pin_memory()
 
@@ -501,6 +539,15 @@ class SlabGroup:
         for stage in range(self.slabs[0].n_stages()):
             for s in self.slabs:
                 s.frame_stage(stage)
+        # a wait that gave up (4 s watchdog of k_signal_wait) means stale halo rows: never render on silently.  The
+        # status read synchronises the stream, so it is taken every 64th frame only.
+        self._frames = getattr(self, "_frames", 0) + 1
+        if self._frames % 64 == 0:
+            self.check()
+
+    def close(self):
+        for s in self.slabs:
+            s.close()
 
     def reset_history(self):
         for s in self.slabs:

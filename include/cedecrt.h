@@ -242,8 +242,13 @@ int crt_reservoir_import_aos(crt_ctx* ctx, int width, int height, crt_buffer aos
  * ranks by any host channel), opens its neighbours' handles and registers the peer pointers with
  * crt_slab_set_links.  crt_slab_exchange then replaces the host-side halo exchange between the stages of the fused
  * frame: it stores this rank's 87 boundary rows of the chosen buffer into the neighbours' buffers over NVLink,
- * signals them, and waits for their rows (csrc/slab_p2p.cu).  Slabs must be at least 87 rows tall and the image
- * width a multiple of 16; otherwise exchange the rows on the host side (python/slabs.py does it with NCCL). */
+ * signals them, and waits for their rows (csrc/slab_p2p.cu).  Constraints, all checked (CRT_EINVAL): slabs at least
+ * 87 rows tall, image width a multiple of 16, spatial_resampling_radius <= 30 (the mirrored band is 87 rows: the
+ * reach of radius 30), options that run the fused bodies (crt_restir_is_fused), and 0 or >= 2 spatial passes — the
+ * one signal/wait per pass is the only ordering between neighbours, and with a single pass a neighbour's next frame
+ * could overwrite halo rows this slab is still reading.  Anything else: exchange the rows on the host side
+ * (python/slabs.py does it with NCCL).  Unmap the neighbours' buffers (crt_slab_set_links(NULL), crt_ipc_close) before
+ * any rank frees the buffers it exported. */
 int crt_ipc_export(crt_ctx* ctx, void* device_ptr, unsigned char handle_out[64]);
 int crt_ipc_open(crt_ctx* ctx, const unsigned char handle[64], void** peer_ptr_out);
 int crt_ipc_close(crt_ctx* ctx, void* peer_ptr);
@@ -258,7 +263,8 @@ typedef struct
     void* down[4];
     void* up_flag;   /* 8-byte slot this rank raises in the upper neighbour's flag buffer (its slot 1) */
     void* down_flag; /* ... in the lower neighbour's flag buffer (its slot 0) */
-    void* my_flags;  /* this rank's own flag buffer: 16 zeroed bytes; slot 0 is raised by `up`, slot 1 by `down` */
+    void* my_flags;  /* this rank's own flag buffer: 32 zeroed bytes — slot 0 (raised by `up`), slot 1 (raised by `down`),
+                      * the 8-byte time-out mark crt_slab_status reads, 8 bytes reserved */
 } crt_slab_links;
 int crt_slab_set_links(crt_ctx* ctx, const crt_slab_links* links);
 /* Call between the stages of the fused frame, before the spatial pass that reads buffer `which` (0 temporal,

@@ -53,6 +53,33 @@ def test_halo_plan_is_symmetric_and_sufficient():
             assert (got | ~need).all()  # every row a neighbour lookup can touch is present
 
 
+def test_halo_rows_bound_the_neighbour_reach():
+    """slabs.halo_rows(radius) (and csrc/restir_fast.cuh: halo_rows_for, the same formula) bounds |neighbour - pixel|
+    for every random pair the reference can draw: rv0 in {2^-23 ... 1 - 2^-23}, any angle (reservoir.hpp:89-95,
+    10_restir_di.cu:309-313: float arithmetic, truncation towards zero)."""
+    assert slabs.halo_rows(30.0) == slabs.HALO == 87
+    rv0 = np.float32(2.0 ** -23)  # the smallest non-zero uniformf() value gives the longest offset
+    phi = np.linspace(0, 2 * np.pi, 100001).astype(np.float32)
+    for radius in (1.0, 7.5, 30.0, 64.0, 200.0):
+        r = np.sqrt(np.maximum(np.float32(-2.0) * np.log(rv0), np.float32(0)), dtype=np.float32)
+        gx = r * np.cos(phi, dtype=np.float32)
+        for yi in (0, 1, 500, 2159):
+            y = (np.float32(yi) + np.float32(radius) / np.float32(1.96) * gx).astype(np.float32)
+            reach = np.abs(np.trunc(y).astype(np.int64) - yi).max()
+            assert reach <= slabs.halo_rows(radius), (radius, yi, reach)  # towards smaller y the truncation rounds the reach up
+        assert slabs.halo_rows(radius) <= int(radius / 1.96 * 5.65) + 2  # and it is tight
+
+
+def test_halo_plan_with_a_wider_reach():
+    H, world = 2160, 8
+    edges = [slabs.slab_rows(H, world, r)[0] for r in range(world)] + [H]
+    wide = slabs.halo_rows(120.0)  # 346 rows: beyond the adjacent slab (270 rows)
+    plan = slabs.halo_plan(H, edges, 3, wide)
+    assert sorted(p[0] for p in plan) == [1, 2, 4, 5]
+    covered = sorted(r for _, _, recv in plan for r in range(*recv))
+    assert covered[0] == edges[3] - wide and covered[-1] == edges[4] + wide - 1
+
+
 def test_planar_row_ranges_select_exactly_the_rows(emu_lib):
     W, H = 16, 40
     n = W * H
