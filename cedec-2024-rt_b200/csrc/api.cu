@@ -77,7 +77,8 @@ extern "C" const char* crt_device_name(crt_ctx* ctx) { return ctx ? ctx->name : 
 extern "C" int crt_set_math_mode(crt_ctx* ctx, int mode)
 {
     CRT_REQUIRE(ctx, "null context");
-    CRT_REQUIRE(mode == CRT_MATH_LIBDEVICE || mode == CRT_MATH_EXACT || mode == CRT_MATH_FAST, "unknown math mode");
+    CRT_REQUIRE(mode == CRT_MATH_LIBDEVICE || mode == CRT_MATH_EXACT || mode == CRT_MATH_FAST || mode == CRT_MATH_REFERENCE,
+                "unknown math mode");
     ctx->math_mode = mode;
     return CRT_OK;
 }

@@ -16,7 +16,7 @@ struct crt_ctx
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // the stream every launch and copy goes to
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-    int math_mode = CRT_MATH_LIBDEVICE;
+    int math_mode = CRT_MATH_REFERENCE;
     int sm_count = 0;
     char name[256] = {0};
     // wavefront shadow rays (shadow_queue.cuh): ray queue + {count, next} counters, grown on demand

@@ -20,13 +20,22 @@
 // per-kernel path of kernels_dropin.cu on AoS buffers instead — same results, reference data flow.
 #include "launch_common.cuh"
 
-// This file is compiled twice (csrc/Makefile).  The regular object carries the host API and the per-pixel kernels in
-// namespace crt::ex, compiled like the rest of the library (-fmad=false, IEEE division and square root: the arithmetic
-// the CPU oracle checks bit for bit).  The second object (-DCRT_FASTMATH_TU -use_fast_math) carries only the per-pixel
-// kernels again, in namespace crt::fm: CRT_MATH_FAST.  Traversal and the triangle test are not in these kernels
-// (shadow rays are queued, primary rays are k_raycast), so they stay exact in every mode.
+// This file is compiled three times (csrc/Makefile).  The regular object carries the host API and the per-pixel kernels
+// in namespace crt::ex, compiled like the rest of the library (-fmad=false, IEEE division and square root: the
+// arithmetic the CPU oracle checks bit for bit; CRT_MATH_LIBDEVICE and CRT_MATH_EXACT).  The other two carry only the
+// per-pixel kernels again:
+//   crt::rf  -DCRT_REFMATH_TU   -fmad=true, IEEE division / square root, libdevice functions — nvcc's and NVRTC's
+//                               defaults, i.e. the arithmetic of the reference's own GPU build (10_restir_di.cpp:56-70
+//                               passes no floating-point option): CRT_MATH_REFERENCE, the default mode;
+//   crt::fm  -DCRT_FASTMATH_TU  -use_fast_math: CRT_MATH_FAST.
+// Traversal and the triangle test are not in these kernels (shadow rays are queued, primary rays are k_raycast), so
+// they stay exact in every mode.
 #if defined(CRT_FASTMATH_TU)
 #define CRT_KNS fm
+#define CRT_AUX_TU 1
+#elif defined(CRT_REFMATH_TU)
+#define CRT_KNS rf
+#define CRT_AUX_TU 1
 #else
 #define CRT_KNS ex
 #endif
@@ -122,7 +131,7 @@ int preload()
 }
 }  // namespace CRT_KNS
 
-#if !defined(CRT_FASTMATH_TU)
+#if !defined(CRT_AUX_TU)
 namespace fm
 {
 int preload();
@@ -135,6 +144,20 @@ void launch_spatial(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows r
 void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H, Rows rows, const float* tris60,
                     const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q, int accumulate, int reuse_traced);
 }  // namespace fm
+namespace rf
+{
+int preload();
+void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
+                               const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
+                               const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
+                               ShadowQueue q, HaloPeers peers);
+void launch_spatial(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye,
+                    crt_options options, SoaStore in, SoaStore out, GBuf g, HaloPeers peers);
+void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H, Rows rows, const float* tris60,
+                    const crt_visibility* vis, SoaStore res, GBuf g, ShadowQueue q, int accumulate, int reuse_traced);
+}  // namespace rf
+// the namespace whose kernels implement the context's math mode
+#define CRT_MODE_NS(ctx, fn) ((ctx)->math_mode == CRT_MATH_FAST ? fm::fn : (ctx)->math_mode == CRT_MATH_REFERENCE ? rf::fn : ex::fn)
 // the traced marks of a history buffer stop being true when the geometry they were traced against is replaced
 // Only this context's own rows (pixels [first, first + n) of the bottom-up buffer): with slab links set, the halo rows
 // of the buffer are stored into by the neighbours' kernels — and rewritten by them in full every frame, marks included —
@@ -156,7 +179,8 @@ int preload_fused_kernels()
     CRT_CUDA(cudaFuncGetAttributes(&a, k_trace_shadow_queue<kEpiSoaVisibility>));
     CRT_CUDA(cudaFuncGetAttributes(&a, k_trace_shadow_queue<kEpiResolve>));
     CRT_CUDA(cudaFuncGetAttributes(&a, k_build_light_table));
-    const int rc = ex::preload();
+    int rc = ex::preload();
+    if (rc == CRT_OK) rc = rf::preload();
     return rc != CRT_OK ? rc : fm::preload();
 }
 // layout conversion for inspection / parity dumps / switching modes with history
@@ -168,10 +192,10 @@ __global__ void __launch_bounds__(256) k_aos_to_soa(size_t n, const crt_reservoi
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) aos_to_soa(aos, s, (int)i);
 }
-#endif  // !CRT_FASTMATH_TU (the namespace closes in both builds)
+#endif  // !CRT_AUX_TU (the namespace closes in every build)
 }  // namespace crt
 
-#if !defined(CRT_FASTMATH_TU)
+#if !defined(CRT_AUX_TU)
 using namespace crt;
 
 namespace
@@ -330,7 +354,7 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
         rc = light_table_for(ctx, geom, tris60, (const uint32_t*)lights.data, n_lights, &table);
         if (rc != CRT_OK) return rc;
     }
-    (ctx->math_mode == CRT_MATH_FAST ? fm::launch_candidate_temporal : ex::launch_candidate_temporal)(
+    CRT_MODE_NS(ctx, launch_candidate_temporal)(
         ctx->stream, exact, grid, W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), table,
         (const uint32_t*)lights.data, n_lights, options, T, g, q, peers);
     rc = check_launch(ctx, "candidate_temporal");
@@ -368,7 +392,7 @@ extern "C" int crt_restir_spatial_pass(crt_ctx* ctx, int W, int H, int frame, in
     pass_buffers(b, pass, &in, &out);
     // the last pass's output is only read by this rank's resolve: nothing to mirror
     const HaloPeers peers = pass + 1 < options.spatial_resampling_passes ? halo_peers(ctx, which_of(b, out), rows, false, n) : HaloPeers();
-    (ctx->math_mode == CRT_MATH_FAST ? fm::launch_spatial : ex::launch_spatial)(
+    CRT_MODE_NS(ctx, launch_spatial)(
         ctx->stream, ctx->math_mode == CRT_MATH_EXACT, tile_grid(W, rows), W, H, rows, frame, pass, geom->view(), to_f3(eye),
         options, soa(in, n), soa(out, n), g, peers);
     return check_launch(ctx, "spatial_fast");
@@ -399,7 +423,7 @@ extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geo
     rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
     if (rc != CRT_OK) return rc;
     crt_float4* accum = (crt_float4*)b->accumulation.data;
-    (ctx->math_mode == CRT_MATH_FAST ? fm::launch_resolve : ex::launch_resolve)(
+    CRT_MODE_NS(ctx, launch_resolve)(
         ctx->stream, tile_grid(W, rows), accum, W, H, rows, (const float*)triangles.data,
         (const crt_visibility*)b->visibility.data, soa(fin, n), g, q, options.accumulate,
         ctx->resolve_reuse && options.use_visibility_reuse);
@@ -444,4 +468,4 @@ extern "C" int crt_reservoir_import_aos(crt_ctx* ctx, int W, int H, crt_buffer a
     k_aos_to_soa<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (const crt_reservoir*)aos_in.data, soa(soa_storage, n));
     return check_launch(ctx, "aos_to_soa");
 }
-#endif  // !CRT_FASTMATH_TU
+#endif  // !CRT_AUX_TU

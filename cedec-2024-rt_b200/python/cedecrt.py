@@ -28,7 +28,7 @@ RESERVOIR = np.dtype(  # reservoir.hpp:5-38
 FLOAT4 = np.dtype((np.float32, (4,)))
 assert TRIANGLE.itemsize == 60 and VISIBILITY.itemsize == 16 and RESERVOIR.itemsize == 76
 
-MATH_LIBDEVICE, MATH_EXACT, MATH_FAST = 0, 1, 2
+MATH_LIBDEVICE, MATH_EXACT, MATH_FAST, MATH_REFERENCE = 0, 1, 2, 3  # include/cedecrt.h: CRT_MATH_*
 
 
 class Float3(C.Structure):
@@ -286,7 +286,7 @@ class Geometry:
 class Runtime:
     """One context per GPU (crt_ctx): replaces the Orochi device/context/stream set-up of 10_restir_di.cpp:30-53."""
 
-    def __init__(self, device=0, math_mode=MATH_LIBDEVICE):
+    def __init__(self, device=0, math_mode=MATH_REFERENCE):
         self.lib = lib()
         ctx = C.c_void_p()
         rc = self.lib.crt_init(device, C.byref(ctx))

@@ -475,7 +475,7 @@ class SlabGroup:
         # builds the shared geometry's light records and has every kernel of the frame loaded (with lazy module loading
         # a first launch waits for the device to go idle, which it never would under a spinning wait kernel).
         first = self.slabs[0]
-        for mode in (first.c.MATH_FAST, first.c.MATH_LIBDEVICE):
+        for mode in (first.c.MATH_FAST, first.c.MATH_LIBDEVICE, first.c.MATH_REFERENCE):
             first.rt.set_math_mode(mode)
             first.rt.restir_di_frame(W, H, 1, first.geom, first.triangles, first.raygen, first.eye, first.lights,
                                      first.options, first.bufs)

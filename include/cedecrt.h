@@ -71,17 +71,26 @@ enum
     CRT_ESTACK = 5     /* BVH deeper than the traversal stack */
 };
 
-/* numerics of the transcendental functions inside the kernels (log/sin/cos in the Gaussian neighbour
- * draw, exp/pow in the rejection heuristics, pow in tone mapping and AO):
- *   CRT_MATH_LIBDEVICE  CUDA's float functions — what the reference's NVRTC build computes. Default.
- *   CRT_MATH_EXACT      correctly rounded via double; bit-identical to the CPU oracle's mode 1.
+/* arithmetic of the per-pixel kernels (Box-Muller log/sin/cos of the neighbour draw, exp/pow of the rejection
+ * heuristics, pow in tone mapping and AO, and whether a*b+c is contracted).  Ray traversal and the triangle test are
+ * outside all of this: they run the reference's test operation for operation in every mode, so primitive ids and
+ * hit/no-hit never depend on the mode.
+ *   CRT_MATH_REFERENCE  fused frame: FMA contraction, IEEE division and square root, CUDA's libdevice functions —
+ *                       nvcc's and NVRTC's defaults, i.e. the arithmetic of the reference's own GPU build
+ *                       (10_restir_di.cpp:56-70 passes no floating-point option).  Default.  The per-kernel entry
+ *                       points treat it as LIBDEVICE.  Against the CPU oracle: radiance inside the north star's
+ *                       tolerance (mean relative L1 <= 1e-3 after 64 frames; tests/test_gpu_parity.py).
+ *   CRT_MATH_LIBDEVICE  libdevice functions with every + - * / rounded once in source order (no contraction): the
+ *                       CPU oracle's own arithmetic up to the last ulp of its libm calls.
+ *   CRT_MATH_EXACT      as LIBDEVICE with correctly rounded transcendentals (via double); bit-identical to the CPU
+ *                       oracle's mode 1 — the mode of every bit-exact parity test.
  *   CRT_MATH_FAST       fused frame only (the per-kernel entry points treat it as LIBDEVICE): the reservoir kernels
  *                       (candidates + temporal, spatial passes, resolve's shading) run with FMA contraction, approximate
  *                       division / square root and the hardware exp2/log2/sin/cos approximations.  Rays are still
  *                       traced and triangles tested with the exact arithmetic, so primitive ids are unaffected; radiance
  *                       stays inside the north star's tolerance (mean relative L1 <= 1e-3 after 64 frames, measured
  *                       ~1e-5: tests/test_gpu_parity.py) but is no longer bit-comparable with the oracle. */
-enum { CRT_MATH_LIBDEVICE = 0, CRT_MATH_EXACT = 1, CRT_MATH_FAST = 2 };
+enum { CRT_MATH_LIBDEVICE = 0, CRT_MATH_EXACT = 1, CRT_MATH_FAST = 2, CRT_MATH_REFERENCE = 3 };
 
 /* ---- context, memory, timing ------------------------------------------------------------------ */
 /* replaces oroInitialize/oroInit/oroDeviceGet/oroCtxCreate/oroStreamCreate (10_restir_di.cpp:30-53) */

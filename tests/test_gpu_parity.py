@@ -249,10 +249,12 @@ def test_restir_default_math_within_tolerance(rt, port):
 
 
 def test_fast_math_mode_within_tolerance_over_64_frames(rt, port):
-    """CRT_MATH_FAST (reservoir kernels with FMA contraction, approximate division, hardware transcendentals; rays and
-    triangle tests exact): 64 accumulated frames of the fused frame on the config-4/5 scene and camera against the
-    oracle.  Bars: primitive ids bit-exact; accumulated radiance within the north star's mean relative L1 <= 1e-3
-    (measured 6e-5, profiles/r1/long_horizon_parity.txt); the default mode on the same run stays below 1e-6."""
+    """The contracted-arithmetic modes of the fused frame — CRT_MATH_REFERENCE (the default: FMA contraction, IEEE
+    division / square root, libdevice functions = the reference's own NVRTC arithmetic) and CRT_MATH_FAST (approximate
+    division, hardware transcendentals) — with rays and triangle tests exact in both: 64 accumulated frames on the
+    config-4/5 scene and camera against the oracle.  Bars: primitive ids bit-exact; accumulated radiance within the
+    north star's mean relative L1 <= 1e-3 (FAST measured 6e-5, profiles/r1/long_horizon_parity.txt); the uncontracted
+    LIBDEVICE mode on the same run stays below 1e-6."""
     tris = staged("blocks_restir")
     W, H, N = 480, 270, 64
     kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
@@ -260,7 +262,7 @@ def test_fast_math_mode_within_tolerance_over_64_frames(rt, port):
     ch = orc.RestirChain(port, W, H, tris, g, *CAM_RESTIR, orc.make_options(**kw))
     apps = {}
     try:
-        for mode in (cedecrt.MATH_FAST, cedecrt.MATH_LIBDEVICE):
+        for mode in (cedecrt.MATH_FAST, cedecrt.MATH_REFERENCE, cedecrt.MATH_LIBDEVICE):
             rt.set_math_mode(mode)
             apps[mode] = cedecrt.RestirDI(rt, W, H, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
         for _ in range(N):
@@ -274,8 +276,10 @@ def test_fast_math_mode_within_tolerance_over_64_frames(rt, port):
             assert same(app.visibility.to_host()["index"], ch.vis["index"])
             assert same(acc[:, 3], ch.accum[:, 3]) and np.isfinite(acc).all()
             err[mode] = rel_l1(acc, ch.accum)
-        print("mean relative L1 after %d frames: fast %.3e, libdevice %.3e" % (N, err[cedecrt.MATH_FAST], err[cedecrt.MATH_LIBDEVICE]))
+        print("mean relative L1 after %d frames: fast %.3e, reference %.3e, libdevice %.3e" % (
+            N, err[cedecrt.MATH_FAST], err[cedecrt.MATH_REFERENCE], err[cedecrt.MATH_LIBDEVICE]))
         assert err[cedecrt.MATH_FAST] <= REL_L1_TOL
+        assert err[cedecrt.MATH_REFERENCE] <= REL_L1_TOL
         assert err[cedecrt.MATH_LIBDEVICE] <= 1e-6
     finally:
         rt.set_math_mode(cedecrt.MATH_LIBDEVICE)
