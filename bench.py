@@ -20,6 +20,14 @@ fast_math = the same K frames with crt_set_math_mode(CRT_MATH_FAST), reported be
          reservoir kernels with fast math, rays and triangle tests exact, radiance 6e-5 from the oracle after 64 frames.
 roofline = the dominant kernel by time (a traversal kernel: issue-bound), `traffic` from the
          committed ncu capture; roofline_reservoir_passes = the reservoir kernels' algorithmic bytes / their time.
+ref_gpu = the reference's own Orochi/HIPRT CUDA build of 10_restir_di (baseline/_ref/bin/ref_gpu: its unmodified kernel file
+         compiled by NVRTC at run time, HIPRT's traversal) on the same GPU, same scene, camera, options and frame count, event-timed
+         around the same kernel list (10_restir_di.cpp:254-255,382-383) — run by rank 0 at N = 1 after the timed regions.
+frame_hash = after the timed regions: history reset, CRT_MATH_EXACT, frames 1-2 rendered again, the RGBA8 image and the float4
+         accumulation hashed row by row (a partition-independent checksum of checksums): the same value at N = 1, 2, 4, 8 and the
+         one tests/test_gpu_parity.py::test_bench_frame_hash asserts.
+--config 06 | 08 | 09 : BASELINE configs 2-4 (06_ao_hiprt on blocks_ao, 08_nee on blocks_pt, 09_ris with the shadowed target on
+         blocks_restir, all 1920x1080) instead of config 5: Mpix/s and Grays/s of the single-kernel frame.
 N > 1  : the frame is split into horizontal row slabs, one rank per GPU (strong scaling); scene and BVH are
          replicated; the 87 halo rows of reservoirs the spatial passes read are stored by the producing rank
          directly into its neighbours' buffers over NVLink (--halo p2p, csrc/slab_p2p.cu) or exchanged with
@@ -48,29 +56,46 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1", "ncu_q_summary.csv")  # committed `ncu --set full` capture, N = 1, 4K
+# committed `ncu --set full` capture of this command (N = 1, 4K, default mode): newest round first
+NCU_SUMMARY = next((q for q in (os.path.join(ROOT, "profiles", "r2", "ncu_r2_summary.csv"),
+                                os.path.join(ROOT, "profiles", "r1", "ncu_q_summary.csv")) if os.path.exists(q)), "")
 NCU_NAMES = {"raycast": "k_raycast", "candidate_temporal": "k_candidate_temporal", "spatial_fast": "k_spatial_fast",
              "resolve_fast": "k_resolve_fast", "tone_mapping": "k_tone_mapping",
              "trace_visibility_reuse": "k_trace_shadow_queue<2>", "trace_resolve": "k_trace_shadow_queue<1>"}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed capture (bytes), or None"""
+def _ncu_rows(kernel):
     import csv
 
-    key = NCU_NAMES.get(kernel)
-    if not key or not os.path.exists(NCU_SUMMARY):
-        return None
+    key = NCU_NAMES.get(kernel, kernel)
+    if not key or not NCU_SUMMARY:
+        return None, None, None
     rows = list(csv.reader(open(NCU_SUMMARY)))
-    h = rows[0]
+    return rows[0], rows[1], [r for r in rows[2:] if key in r[0]]
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed capture (bytes), or None"""
+    h, units, rows = _ncu_rows(kernel)
+    if not rows:
+        return None
     try:
         ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
     except ValueError:
         return None
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    vals = [float(r[ir]) * scale.get(rows[1][ir], 1.0) + float(r[iw]) * scale.get(rows[1][iw], 1.0)
-            for r in rows[2:] if key in r[0]]
+    vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in rows]
     return int(sum(vals) / len(vals)) if vals else None
+
+
+def ncu_warp_instructions(kernel):
+    """smsp__inst_executed.sum per launch of `kernel` from the committed capture (warp instructions), or None"""
+    h, units, rows = _ncu_rows(kernel)
+    if not rows or "smsp__inst_executed.sum" not in h:
+        return None
+    i = h.index("smsp__inst_executed.sum")
+    vals = [float(r[i]) for r in rows]
+    return sum(vals) / len(vals)
 
 
 class ClockSampler:
@@ -153,7 +178,132 @@ HBM_BOUND = ("temporal_resampling", "save_temporal_reservoir", "spatial_resampli
              "candidate_temporal", "resolve_fast")
 
 
+# ============================================================================================== frame hash
+def _row_weights(np, n_words):
+    """odd 64-bit multipliers K_i = splitmix64(i) | 1 (numpy uint64 arithmetic wraps modulo 2^64)"""
+    with np.errstate(over="ignore"):
+        z = (np.arange(n_words, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z | np.uint64(1)).view(np.int64)
+
+
+def frame_hash(torch, dist, r, world, frames=2):
+    """Partition-independent fingerprint of the rendered frame, bit-stable across builds: history reset, CRT_MATH_EXACT
+    (every operation rounded once in source order, correctly rounded transcendentals — bit-identical to the CPU oracle),
+    `frames` frames of the benchmarked loop, then for every image row yi the wrap-around sums
+    sum_i word_i * K_i (mod 2^64) over the row's RGBA8 words and over its float4 accumulation words, and FNV-1a-64 over
+    those 2 H values in row order.  Every row is hashed by the rank (slab) that rendered it."""
+    import numpy as np
+
+    import cedecrt
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    r.join()
+    barrier()
+    r.set_math_mode(cedecrt.MATH_EXACT)
+    r.reset_history()
+    barrier()
+    for _ in range(frames):
+        r.frame()
+    r.join()
+    barrier()
+    first = r.slabs[0]
+    W, H = first.W, first.H
+    rows = torch.zeros((H, 2), dtype=torch.int64, device="cuda")
+    for sl in r.slabs:
+        if sl.y1 <= sl.y0:
+            continue
+        for col, (t, elem) in enumerate(((sl.t_pix, 4), (sl.t_acc, 16))):
+            words = sl._rows(t, elem, sl.y0, sl.y1).view(torch.int32).reshape(sl.y1 - sl.y0, -1).to(torch.int64)
+            k = torch.from_numpy(_row_weights(np, words.shape[1])).to(words.device)
+            h = (words * k).sum(dim=1)  # int64 arithmetic wraps: sums modulo 2^64
+            rows[sl.y0:sl.y1, col] = torch.flip(h, dims=[0])  # bottom-up storage: the slab's last row comes first
+    if world > 1:
+        dist.all_reduce(rows)  # every row was filled by exactly one slab
+    data = rows.cpu().numpy().astype("<i8").tobytes()
+    h = 0xCBF29CE484222325
+    for b in data:
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return {"value": "%016x" % h, "frames": frames, "math": "exact",
+            "recipe": "FNV-1a-64 over per-row (RGBA8, accumulation) wrap-around weighted word sums, rows in yi order"}
+
+
+# ============================================================================================== reference GPU comparator
+def run_ref_gpu(W, H, steps, warmup, tiles=(3, 2), timeout=900):
+    """the reference's own Orochi/HIPRT CUDA build of examples/10_restir_di on this GPU (baseline/_ref/bin/ref_gpu, built
+    by `make -C oracle refgpu` from the reference's sources; see oracle/ref_gpu/ref_gpu_main.cpp): same scene, tiling,
+    camera, options and frame count, OroStopwatch around the kernel list like 10_restir_di.cpp:254-255,382-383."""
+    import lzma
+    import tempfile
+
+    bin_dir = os.path.join(ROOT, "baseline", "_ref", "bin")
+    exe = os.path.join(bin_dir, "ref_gpu")
+    src = os.path.join(ROOT, "assets", "blocks_restir.tri.xz")
+    if not os.path.exists(exe):
+        return {"unavailable": "baseline/_ref/bin/ref_gpu not staged (make -C oracle refgpu needs /root/reference)"}
+    if not os.path.exists(src):
+        return {"unavailable": "assets/blocks_restir.tri.xz not staged"}
+    t0 = time.time()
+    tmp = tempfile.mkdtemp(prefix="refgpu_")
+    tri = os.path.join(tmp, "blocks_restir.tri")
+    with lzma.open(src, "rb") as f, open(tri, "wb") as g:
+        g.write(f.read())
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = bin_dir + ":/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    cmd = [exe, "--base", "../", "--tri", tri, "--width", str(W), "--height", str(H), "--tiles-x", str(tiles[0]),
+           "--tiles-z", str(tiles[1]), "--frames", str(steps), "--warmup", str(warmup)]
+    try:
+        pr = subprocess.run(cmd, cwd=bin_dir, env=env, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "timed out after %d s" % timeout}
+    finally:
+        try:
+            os.remove(tri)
+            os.rmdir(tmp)
+        except OSError:
+            pass
+    line = [l for l in pr.stdout.splitlines() if l.startswith("{")]
+    if not line:
+        return {"unavailable": "exit code %d, no result line; stderr tail: %s" % (pr.returncode, pr.stderr[-300:].replace("\n", " | "))}
+    out = json.loads(line[-1])
+    if "unavailable" in out:
+        return {"unavailable": out["unavailable"]}
+    return {"value": out["value"], "unit": "Mpix/s", "ms_per_step": out["ms_per_step"], "steps": out["steps"], "warmup": out["warmup"],
+            "build_s": out.get("geometry_build_s"), "compile_s": out.get("trace_kernel_compile_s"),
+            "mean_radiance": out.get("mean_radiance"), "sky_pixels": out.get("sky_pixels"), "wall_s": round(time.time() - t0, 1),
+            "what": "reference Orochi/HIPRT build (HIPRT 2.4 binary, kernels JIT-compiled by NVRTC from the unmodified "
+                    "10_restir_di.cu), same GPU, scene, camera, options; CUDA-event time of raycast ... tone_mapping per frame"}
+
+
 from slabs import HALO as HALO_ROWS, SlabGroup, SlabRenderer  # noqa: E402  (cedec-2024-rt_b200/python/slabs.py)
+
+
+def dominant_roofline(name, k, hbm_peak, peak_src, issue_peak, sm_mhz, comparable):
+    """`roofline` of the JSON line: the dominant kernel by time against the roof that bounds it.  The traversal kernels
+    (raycast, trace_*) issue instructions at ~75 % of the schedulers' rate with < 5 % of DRAM bandwidth: their roof is
+    instruction issue; the per-pixel reservoir kernels are measured against HBM (roofline_reservoir_passes)."""
+    traversal = name in ("raycast", "trace_visibility_reuse", "trace_resolve")
+    hbm = {"achieved": k.get("algo_gbs"), "peak": hbm_peak, "unit": "GB/s",
+           "frac": round(k["algo_gbs"] / hbm_peak, 4) if k.get("algo_gbs") else None, "peak_source": peak_src}
+    out = {"kernel": name, "traffic": ncu_traffic(name) if comparable else None,
+           "traffic_source": (os.path.relpath(NCU_SUMMARY, ROOT) + " (dram__bytes_read.sum + dram__bytes_write.sum, one launch)") if NCU_SUMMARY else None}
+    if traversal and "issue_frac" in k:
+        out.update({"bound": "issue", "achieved": round(k["warp_inst_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9, 2),
+                    "peak": round(issue_peak / 1e9, 2), "unit": "Gwarp-inst/s", "frac": k["issue_frac"], "hbm": hbm,
+                    "note": "dominant kernel by time; a traversal kernel: bound by instruction issue (148 SMs x 4 schedulers x "
+                            "%.0f MHz sampled in this run), not by HBM — its algorithmic bytes against the HBM peak are kept under "
+                            "`hbm` for reference" % sm_mhz})
+    else:
+        out.update({"bound": "hbm", **hbm,
+                    "note": "dominant kernel by time" + ("; a traversal kernel (issue-bound: see profiles/ for the ncu capture; no "
+                            "instruction count for this configuration is committed, so only the HBM figure is given)" if traversal else "")})
+    return out
 
 
 def pixel_classes(torch, renderer):
@@ -220,6 +370,10 @@ def run_cuda(args):
         if world > 1:
             dist.all_reduce(bad)
         if bad.item() > 0:
+            r.close()  # unmap the neighbours' buffers ...
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()  # ... on every rank before any rank frees what it exported
             r, sub = None, 1
         else:
             r.reset_history()
@@ -227,8 +381,11 @@ def run_cuda(args):
     if r is None:
         r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
     import cedecrt
-    r.set_math_mode({"libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_FAST, "exact": cedecrt.MATH_EXACT}[args.math])
+    math_mode = {"reference": cedecrt.MATH_REFERENCE, "libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_FAST,
+                 "exact": cedecrt.MATH_EXACT}[args.math]
+    r.set_math_mode(math_mode)
     stats = r.geom.stats()
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     if world * sub > 1 and not args.no_balance:
         r.calibrate(rounds=3, frames=4)  # static camera: balance the slab heights on throw-away frames before the sequence starts
 
@@ -305,7 +462,7 @@ def run_cuda(args):
     # ---- the same K frames in CRT_MATH_FAST (reported next to the headline, never as the headline: its radiance is
     # inside the north star's tolerance of the oracle but not bit-comparable; include/cedecrt.h)
     ms_fast = None
-    if fused and args.math == "libdevice" and not args.no_fast_line:
+    if fused and args.math in ("reference", "libdevice") and not args.no_fast_line:
         r.set_math_mode(cedecrt.MATH_FAST)
         for _ in range(2):
             r.frame()
@@ -318,7 +475,7 @@ def run_cuda(args):
         f1.record()
         barrier()
         ms_fast = f0.elapsed_time(f1)
-        r.set_math_mode(cedecrt.MATH_LIBDEVICE)
+        r.set_math_mode(math_mode)
         r.frame()
     # ---- per-kernel device times: an event after every launch (crt_profile_begin/end), steady-state frames
     n_prof = max(2, min(args.steps, 4))
@@ -338,6 +495,10 @@ def run_cuda(args):
         print("bench.py: %s" % e, file=sys.stderr)
         timed_out = 1.0
     n_px, n_diffuse = pixel_classes(torch, r)
+    fhash = None
+    if not args.no_frame_hash:
+        fhash = frame_hash(torch, dist if world > 1 else None, r, world)
+        r.set_math_mode(math_mode)
     # rays actually traced per frame: 1 primary per pixel + the shadow rays counted by the tracer (the reference traces
     # 2 per diffuse pixel; the fused frame skips those whose answer it already holds, see include/cedecrt.h)
     rays = n_px + sum(shadow_rays)
@@ -378,6 +539,16 @@ def run_cuda(args):
             elif name == "trace_visibility_reuse":
                 k["mrays_per_s"] = round(shadow_rays[0] / per_launch / 1e3, 1)
             kern[name] = k
+        # instruction-issue roofline: warp instructions per launch (committed ncu capture of this command: they do not
+        # depend on the clock) / the live launch time, against SMs x 4 schedulers x the SM clock sampled during this run
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        issue_peak = sm_count * 4 * sm_mhz * 1e6  # warp instructions per second
+        comparable = world == 1 and fused and (W, H) == (W4K, H4K) and args.math == "reference"
+        for name, k in kern.items():
+            inst = ncu_warp_instructions(name) if comparable else None
+            if inst:
+                k["warp_inst_per_launch"] = int(inst)
+                k["issue_frac"] = round(inst / (k["ms_per_launch"] * 1e-3) / issue_peak, 4)
         frame_ms_by_kernel = {k: v["ms_per_launch"] * v["launches_per_frame"] for k, v in kern.items()}
         dominant = max(frame_ms_by_kernel, key=frame_ms_by_kernel.get)
         passes = [k for k in kern if k in HBM_BOUND]
@@ -399,7 +570,9 @@ def run_cuda(args):
                            "(cudaIpc peer pointers, csrc/slab_p2p.cu)" if r.p2p else
                            "%d halo bytes sent per frame by rank 0 (NCCL send/recv)" % halo_bytes_per_frame),
                        "l2": "per-frame working set (3 x 600 MB reservoir buffers) exceeds the 126 MB L2; no flush needed",
-                       "math": {"libdevice": "libdevice float functions, -fmad=false, IEEE division (bit-faithful to the CPU oracle's arithmetic)",
+                       "math": {"reference": "CRT_MATH_REFERENCE: FMA contraction, IEEE division / square root, libdevice functions (nvcc / NVRTC "
+                                             "defaults: the reference's own GPU arithmetic); traversal and triangle tests uncontracted",
+                                "libdevice": "libdevice float functions, -fmad=false, IEEE division (bit-faithful to the CPU oracle's arithmetic)",
                                 "exact": "correctly rounded transcendentals, -fmad=false (bit-identical to the CPU oracle)",
                                 "fast": "CRT_MATH_FAST: reservoir kernels with FMA contraction, approximate division and hardware "
                                         "transcendentals; traversal and triangle tests exact; radiance within the north star's "
@@ -428,15 +601,14 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "halo_wait_timed_out": bool(any_timed_out),  # true = a slab gave up waiting for a neighbour: the run is invalid
             "clocks": clocks,
-            "roofline": {"kernel": dominant, "bound": "hbm",
-                         "achieved": dom.get("algo_gbs"), "peak": peak, "unit": "GB/s",
-                         "frac": round(dom["algo_gbs"] / peak, 4) if dom.get("algo_gbs") else None,
-                         "traffic": ncu_traffic(dominant) if (world == 1 and fused and (W, H) == (W4K, H4K)) else None,
-                         "traffic_source": "profiles/r1/ncu_q_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
-                         "peak_source": peak_src,
-                         "note": "dominant kernel by time. Traversal kernels (raycast, trace_*) are SM-issue-bound, not "
-                                 "HBM-bound: see profiles/ for issue utilisation and L1/L2 hit rates; the HBM-bound "
-                                 "kernels are summarised in roofline_reservoir_passes"},
+            "roofline": dominant_roofline(dominant, dom, peak, peak_src, issue_peak, sm_mhz, comparable),
+            "roofline_issue": {"peak_warp_inst_per_s": issue_peak, "sm_count": sm_count, "schedulers_per_sm": 4, "sm_mhz": sm_mhz,
+                               "frame_frac": round(sum(k["warp_inst_per_launch"] * k["launches_per_frame"] for k in kern.values()
+                                                       if "warp_inst_per_launch" in k) / (ms / args.steps * 1e-3) / issue_peak, 4)
+                               if comparable and any("warp_inst_per_launch" in k for k in kern.values()) else None,
+                               "source": os.path.relpath(NCU_SUMMARY, ROOT) if NCU_SUMMARY else None,
+                               "note": "per kernel: kernels[*].issue_frac = smsp__inst_executed.sum of the committed ncu capture / "
+                                       "live launch time / (SMs x 4 x sampled SM clock)"},
             "roofline_reservoir_passes": {"bound": "hbm", "achieved": round(res_bytes / res_ms / 1e6, 1), "peak": peak,
                                           "unit": "GB/s", "frac": round(res_bytes / res_ms / 1e6 / peak, 4),
                                           "kernels": passes, "ms_per_frame": round(res_ms, 4)},
@@ -444,7 +616,13 @@ def run_cuda(args):
             "pixels": {"slab": n_px, "diffuse": n_diffuse},
             "slab_kernel_ms": [round(x, 4) for x in slab_ms.tolist()],  # per rank: sum of its own kernels per frame
             "bvh": {k: stats[k] for k in ("n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes")},
+            "frame_hash": fhash,
         }
+        if world == 1 and not args.no_ref_gpu and (W, H) == (W4K, H4K):
+            torch.cuda.synchronize()
+            out["ref_gpu"] = run_ref_gpu(W, H, args.steps, args.warmup)
+            if "value" in out["ref_gpu"]:
+                out["ref_gpu"]["vs_ours"] = round(out["value"] / out["ref_gpu"]["value"], 3)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(r, tris, cam, W, H)
         sys.stdout.flush()
@@ -453,6 +631,211 @@ def run_cuda(args):
         dist.barrier()
         dist.destroy_process_group()
 
+
+
+# ============================================================================================== BASELINE configs 2-4
+EXAMPLES = {
+    # 06_ao_hiprt.cpp:95,115 + misc.hpp:217-218 camera; N_Rays as BASELINE config 2 asks (the reference hard-codes 64)
+    "06": dict(scene="blocks_ao", cam=((8.0, 8.0, 8.0), (0.0, 0.0, 0.0)), ao_rays=32, kernel="ao_06", ncu="k_ao",
+               workload="06_ao_hiprt: blocks_ao.obj, 1920x1080, 32 AO rays per hit pixel (pure any-hit traversal)"),
+    # 08_nee.cpp:135-140 camera; max depth 4, accumulate (BASELINE config 3)
+    "08": dict(scene="blocks_pt", cam=((5.983407, 13.970583, -28.553869), (-5.354514, 4.815835, -2.047728)), kernel="path_trace_08",
+               ncu="k_path_trace<8", options=dict(accumulate=1, max_depth=4),
+               workload="08_nee: blocks_pt.obj, 1920x1080, 1 spp per frame, max depth 4, accumulating"),
+    # 09_ris.cpp:149-154 camera; 32 candidates with visibility inside the target function (BASELINE config 4)
+    "09": dict(scene="blocks_restir", cam=CAM, kernel="path_trace_09", ncu="k_path_trace<9",
+               options=dict(accumulate=1, max_depth=6, ris_sample_count=32, use_shadowed_target_function=1),
+               workload="09_ris: blocks_restir.obj, 1920x1080, 32 light candidates per vertex, shadowed target function, max depth 6"),
+}
+
+
+def run_example(args):
+    """--config 06 | 08 | 09: the single-kernel frames of examples 06-09 (kernel + tone mapping for 08/09, as their host
+    loops launch them) at 1920x1080 on the example's own scene and camera.  N > 1: row slabs, no exchange (every pixel
+    is independent).  Rays are counted by the kernels themselves (crt_inline_rays_traced)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cedecrt
+    import scenes
+
+    ex = EXAMPLES[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = (1920, 1080) if (args.width, args.height) == (W4K, H4K) else (args.width, args.height)
+    tris = scenes.load_scene(ex["scene"])
+    math_mode = {"reference": cedecrt.MATH_LIBDEVICE, "libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_LIBDEVICE,
+                 "exact": cedecrt.MATH_EXACT}[args.math]  # the per-kernel entry points know LIBDEVICE and EXACT
+    rt = cedecrt.Runtime(local, math_mode)
+    rt.set_stream(stream.cuda_stream)
+    from slabs import slab_rows
+    y0, y1 = slab_rows(H, world, rank)
+    rt.set_row_range(y0, y1)
+    d_tris = rt.to_device(tris)
+    lights = cedecrt.light_indices(tris)
+    d_lights = rt.to_device(lights) if len(lights) else None  # blocks_ao has no emissive triangle; 06 takes no light list
+    geom = rt.build_geometry(d_tris)
+    stats = geom.stats()
+    raygen = cedecrt.lookat(ex["cam"][0], ex["cam"][1], W, H)
+    n = W * H
+    pixels = rt.buffer(np.uint8, 4 * n)
+    accum = rt.buffer(cedecrt.FLOAT4, n)
+    rt.clear(accum, W, H)
+    opt = cedecrt.Options(**ex.get("options", {}))
+    host = torch.empty(4 * W * max(y1 - y0, 1), dtype=torch.uint8).pin_memory()
+    t_pix = torch.as_tensor(__import__("slabs").CudaArrayView(pixels.ptr, 4 * n), device=torch.device("cuda", local))
+    state = {"frame": 0}
+
+    def frame():
+        state["frame"] += 1
+        if args.config == "06":
+            rt.ao(pixels, raygen, W, H, geom, d_tris, ex["ao_rays"])
+        else:
+            rt.path_trace(int(args.config), W, H, state["frame"], geom, d_tris, d_lights, raygen, opt, accum)
+            rt.tone_mapping(pixels, accum, W, H)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        frame()
+    barrier()
+    launches0, rays0 = rt.launch_count(), rt.inline_rays_traced()
+    sampler.mark_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        frame()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches, rays1 = rt.launch_count() - launches0, rt.inline_rays_traced()
+    rays = [(b - a) / args.steps for a, b in zip(rays0, rays1)]
+    # end to end: the frame plus the device -> host copy of this rank's RGBA8 rows and a stream synchronise
+    # (06_ao_hiprt.cpp / 08_nee.cpp / 09_ris.cpp read back and display every frame)
+    rows_px = t_pix[(H - y1) * W * 4:(H - y0) * W * 4]
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        frame()
+        host[:rows_px.numel()].copy_(rows_px, non_blocking=True)
+        stream.synchronize()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    n_probe = max(0, int((1.5 - (time.time() - sampler.t0)) / max(ms / args.steps / 1e3, 1e-4)))
+    for _ in range(min(n_probe, 2000)):
+        frame()
+    barrier()
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
+    rt.profile_begin()
+    for _ in range(2):
+        frame()
+    marks = rt.profile_end()
+    t = torch.tensor([ms, ms_e2e, rays[0], rays[1]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e, rays = tmax[0].item(), tmax[1].item(), [tsum[2].item(), tsum[3].item()]
+    if rank == 0:
+        per = {}
+        for name, t_ms in marks:
+            per.setdefault(name, []).append(t_ms)
+        kern = {k: {"ms_per_launch": round(sum(v) / len(v), 4)} for k, v in per.items()}
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = sm_count * 4 * sm_mhz * 1e6
+        main_name = "ao_06" if args.config == "06" else "path_trace"
+        inst = ncu_warp_instructions(ex["ncu"]) if world == 1 and (W, H) == (1920, 1080) else None
+        roof = {"kernel": main_name, "bound": "issue", "unit": "Gwarp-inst/s", "peak": round(issue_peak / 1e9, 2),
+                "achieved": None, "frac": None, "traffic": None,
+                "note": "one traversal kernel: bound by instruction issue, not HBM (DRAM throughput of the committed ncu capture "
+                        "is a few percent of peak); warp instructions from the committed capture / live kernel time"}
+        if inst and main_name in kern:
+            roof["achieved"] = round(inst / (kern[main_name]["ms_per_launch"] * 1e-3) / 1e9, 2)
+            roof["frac"] = round(inst / (kern[main_name]["ms_per_launch"] * 1e-3) / issue_peak, 4)
+            h, units, rows = _ncu_rows(ex["ncu"])
+            roof["traffic"] = ncu_traffic(ex["ncu"])
+        out = {
+            "metric": "%s 1080p Mpix/s" % ex["kernel"], "value": round(n * args.steps / ms / 1e3, 3), "unit": "Mpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ex["workload"], "width": W, "height": H, "triangles": int(len(tris)), "lights": int(len(lights)),
+                       "partition": "%d row slab(s), no exchange" % world,
+                       "l2": "one launch per frame over the whole image; scene + BVH (%d MB) exceed nothing: L2-resident for "
+                             "blocks_ao, larger than L2 for blocks_pt / blocks_restir" % ((stats["node_bytes"] + stats["tri_bytes"]) // 2**20),
+                       "math": "libdevice functions, uncontracted arithmetic (the per-kernel entry points' default)"},
+            "grays_per_s": round(sum(rays) * args.steps / ms / 1e6, 4), "rays_per_frame": int(sum(rays)),
+            "rays": {"closest_hit": int(rays[0]), "shadow_or_ao": int(rays[1]),
+                     "note": "per frame, counted by the kernel itself (crt_inline_rays_traced), SURVEY.md section 8d accounting"},
+            "e2e": {"value": round(n * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s", "h2d_bytes_per_step": 132,
+                    "d2h_bytes_per_step": 4 * n, "note": "frame + RGBA8 device->host copy into pinned memory + stream synchronise"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kern,
+            "bvh": {k: stats[k] for k in ("n_nodes", "max_depth", "build_ms", "node_bytes", "tri_bytes")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_example_sample(args.config, ex, tris, W, H)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_example_sample(config, ex, tris, W, H, rows=16):
+    """cpu_baseline for --config 06/08/09: the reference's own kernel as host C++ (oracle/_ref/libref_NN.so, else the
+    port) on a band of `rows` image rows of frame 1, all host threads"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    import orc
+
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_%s.so" % config)) else "port"
+    o = orc.load(kind, int(config))
+    o.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    if kind == "port":
+        o.set_example(int(config))
+    g = o.geom_build(tris)
+    rg = o.lookat(ex["cam"][0], ex["cam"][1], W, H)
+    y0 = (H - rows) // 2
+    o.set_range(y0 * W, (y0 + rows) * W)
+    t0 = time.perf_counter()
+    if config == "06":
+        if kind == "reference":
+            n_rays = 64  # hard-coded in the reference kernel (06_ao_hiprt.cu:71)
+        else:
+            n_rays = ex["ao_rays"]
+        o.ao(W, H, g, tris, rg, n_rays)
+        what = "%d AO rays per hit pixel%s" % (n_rays, " (the reference kernel's hard-coded count; the CUDA arm traces 32)" if n_rays != ex["ao_rays"] else "")
+    else:
+        opt = orc.make_options(**ex.get("options", {}))
+        o.path_trace(W, H, 1, g, tris, orc.light_indices(tris), rg, opt, np.zeros((W * H, 4), np.float32))
+        what = "one path_trace launch"
+    sec = time.perf_counter() - t0
+    o.set_range(0, -1)
+    return {"value": round(rows * W / sec / 1e6, 4), "unit": "Mpix/s", "cores": o.threads(), "kind": kind, "seconds": round(sec, 3),
+            "sample": "frame 1, image rows %d..%d of the %dx%d frame (%d px), %s; BVH build excluded" % (y0, y0 + rows, W, H, rows * W, what)}
 
 # ============================================================================================== CPU arms
 def cpu_band_run(o, tris, cam, W, H, rows, frames, bufs=None):
@@ -511,6 +894,7 @@ def cpu_baseline_sample(r, tris, cam, W, H, rows=64):
     """cpu_baseline of the CUDA arm's JSON line: the reference's CPU implementation timed on this box's host cores
     on a bounded sample (a band of rows of the same frame)."""
     o, kind = load_cpu_oracle()
+    o.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     times, _ = cpu_band_run(o, tris, cam, W, H, rows, frames=[1])
     sec = sum(times.values())
     return {"value": round(rows * W / sec / 1e6, 4), "unit": "Mpix/s", "cores": o.threads(), "kind": kind,
@@ -527,6 +911,8 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     o, kind = load_cpu_oracle()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: ask for every host thread explicitly
+    o.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     tris, cam, workload = load_workload()
     W, H, rows = args.width, args.height, args.cpu_rows
     bufs = None
@@ -576,8 +962,13 @@ def main():
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal-height slabs (no calibration frames)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1, fused mode: halo rows by direct peer stores (default) or NCCL send/recv")
-    ap.add_argument("--math", default="libdevice", choices=["libdevice", "fast", "exact"],
-                    help="arithmetic of the reservoir kernels (include/cedecrt.h: CRT_MATH_*)")
+    ap.add_argument("--math", default="reference", choices=["reference", "libdevice", "fast", "exact"],
+                    help="arithmetic of the reservoir kernels (include/cedecrt.h: CRT_MATH_*); reference = nvcc/NVRTC defaults, "
+                         "the reference's own GPU arithmetic")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference Orochi/HIPRT comparator run (N = 1, 4K)")
+    ap.add_argument("--no-frame-hash", action="store_true", help="skip the exact-mode frame fingerprint")
+    ap.add_argument("--config", default="10", choices=["10", "06", "08", "09"],
+                    help="10: BASELINE config 5 (default); 06 / 08 / 09: configs 2-4 at 1920x1080 (single-kernel frames)")
     ap.add_argument("--readback", default="pipelined", choices=["pipelined", "sync"],
                     help="e2e: overlap each frame's device->host copy with the next frame (default) or copy and "
                          "synchronise after every frame like the reference's loop")
@@ -589,7 +980,10 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
-        run_cuda(args)
+        if args.config != "10":
+            run_example(args)
+        else:
+            run_cuda(args)
 
 
 if __name__ == "__main__":

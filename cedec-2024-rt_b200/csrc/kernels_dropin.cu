@@ -99,21 +99,36 @@ __global__ void __launch_bounds__(256) k_tone_mapping(size_t n, uint32_t* pixels
         pixels[i] = tone_map_rgba8<Math<MODE>>(f4{a.x, a.y, a.z, a.w});
     }
 }
+// rays traced inside the single-kernel examples (crt_inline_rays_traced): one atomic per warp
+__device__ __forceinline__ void count_rays(unsigned long long* counters, uint32_t n_closest, uint32_t n_shadow)
+{
+    const uint32_t c = __reduce_add_sync(0xffffffffu, n_closest), s = __reduce_add_sync(0xffffffffu, n_shadow);
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (c) atomicAdd(counters + 0, (unsigned long long)c);
+        if (s) atomicAdd(counters + 1, (unsigned long long)s);
+    }
+}
 template <int EX, int MODE>
 __global__ void __launch_bounds__(256)
     k_path_trace(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const uint32_t* lights, uint32_t n_lights,
-                 crt_raygen raygen, crt_options options, crt_float4* accum)
+                 crt_raygen raygen, crt_options options, crt_float4* accum, unsigned long long* ray_counters)
 {
     const TilePix t = this_pixel(W, H, rows);
+    uint32_t n = 0;
     if (t.in)
-        px_path_trace<EX, Math<MODE>>(t.px, W, H, frame, bvh, tris60, lights, n_lights, raygen, make_opt(options), accum);
+        n = px_path_trace<EX, Math<MODE>>(t.px, W, H, frame, bvh, tris60, lights, n_lights, raygen, make_opt(options), accum);
+    count_rays(ray_counters, n & 0xffffu, n >> 16);
 }
 template <int MODE>
 __global__ void __launch_bounds__(256)
-    k_ao(uint32_t* pixels, crt_raygen raygen, int W, int H, Rows rows, Bvh bvh, const float* tris60, int n_rays)
+    k_ao(uint32_t* pixels, crt_raygen raygen, int W, int H, Rows rows, Bvh bvh, const float* tris60, int n_rays,
+         unsigned long long* ray_counters)
 {
     const TilePix t = this_pixel(W, H, rows);
-    if (t.in) pixels[t.px.idx] = px_ao<Math<MODE>>(t.px, raygen, W, H, bvh, tris60, n_rays);
+    uint32_t ao_rays = 0;
+    if (t.in) pixels[t.px.idx] = px_ao<Math<MODE>>(t.px, raygen, W, H, bvh, tris60, n_rays, ao_rays);
+    count_rays(ray_counters, t.in ? 1u : 0u, ao_rays);
 }
 // the kernels of this file the fused frame launches (crt_slab_set_links loads them ahead of any spinning wait)
 int preload_dropin_kernels()
@@ -299,6 +314,27 @@ extern "C" int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accu
     return check_launch(ctx, "tone_mapping");
 }
 
+// two 64-bit device counters per context: closest-hit and shadow / AO rays traced by the single-kernel examples
+static int inline_ray_counters(crt_ctx* ctx, unsigned long long** out)
+{
+    if (!ctx->inline_rays)
+    {
+        CRT_CUDA(cudaMalloc((void**)&ctx->inline_rays, 2 * sizeof(unsigned long long)));
+        CRT_CUDA(cudaMemsetAsync(ctx->inline_rays, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    }
+    *out = ctx->inline_rays;
+    return CRT_OK;
+}
+extern "C" int crt_inline_rays_traced(crt_ctx* ctx, unsigned long long out[2])
+{
+    CRT_REQUIRE(ctx && out, "null argument");
+    out[0] = out[1] = 0;
+    if (!ctx->inline_rays) return CRT_OK;
+    CRT_CUDA(cudaMemcpyAsync(out, ctx->inline_rays, 2 * sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CRT_OK;
+}
+
 template <int EX>
 static int path_trace(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
                       crt_buffer lights, crt_raygen raygen, crt_options options, crt_buffer accumulation)
@@ -308,10 +344,13 @@ static int path_trace(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, 
     CRT_CHECK_BUF(accumulation, (size_t)W * H, "accumulation");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(EX == 7 || bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
+    unsigned long long* counters = nullptr;
+    const int rc = inline_ray_counters(ctx, &counters);
+    if (rc != CRT_OK) return rc;
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_path_trace<EX, 1> : k_path_trace<EX, 0>;
     k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data,
                                                (const uint32_t*)lights.data, (uint32_t)bsize(lights), raygen, options,
-                                               (crt_float4*)accumulation.data);
+                                               (crt_float4*)accumulation.data, counters);
     return check_launch(ctx, "path_trace");
 }
 extern "C" int crt_path_trace_07(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
@@ -338,8 +377,11 @@ extern "C" int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int
     CRT_CHECK_BUF(pixels, (size_t)W * H * 4, "pixel");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(n_rays > 0, "n_rays must be positive");
+    unsigned long long* counters = nullptr;
+    const int rc = inline_ray_counters(ctx, &counters);
+    if (rc != CRT_OK) return rc;
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_ao<1> : k_ao<0>;
     k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>((uint32_t*)pixels.data, raygen, W, H, rows_of(ctx, H), geom->view(),
-                                               (const float*)triangles.data, n_rays);
+                                               (const float*)triangles.data, n_rays, counters);
     return check_launch(ctx, "ao_06");
 }

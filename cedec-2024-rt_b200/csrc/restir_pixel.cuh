@@ -237,11 +237,14 @@ CRT_HD DeferredRay px_resolve(const Pix& px, crt_float4* accum, const Bvh& bvh, 
 }
 
 // ---- 07_pt.cu:11-90 (EX = 7), 08_nee.cu:11-129 (EX = 8), 09_ris.cu:11-166 (EX = 9)
+// Returns the rays this pixel traced: closest-hit (camera + bounce rays) in the low 16 bits, shadow rays in the high 16
+// (08_nee 1 + 1 per path vertex; 09_ris 1 + 1, or 1 + 32 + 1 + 1 with the shadowed target function).
 template <int EX, class M>
-CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh, const float* tris60,
-                          const uint32_t* lights, uint32_t n_lights, const crt_raygen& raygen, const Opt& opt,
-                          crt_float4* accum)
+CRT_HD uint32_t px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh, const float* tris60,
+                              const uint32_t* lights, uint32_t n_lights, const crt_raygen& raygen, const Opt& opt,
+                              crt_float4* accum)
 {
+    uint32_t n_closest = 0, n_shadow = 0;
     Pcg rng(hash_pcg3(px.xi, px.yi, frame), 0);
     f3 ro, rd;
     primary_ray(raygen, px, W, H, ro, rd);
@@ -249,6 +252,7 @@ CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh
     for (int depth = 0; depth < opt.max_depth; ++depth)
     {
         Hit h;
+        ++n_closest;
         if (!trace<false>(bvh, ro, rd, 0.0f, kFltMax, h))
         {
             if (EX == 7) radiance = radiance + throughput * opt.sky;
@@ -269,6 +273,7 @@ CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh
             const float r1 = rng.next_f();
             const float r2 = rng.next_f();
             const LightSample ls = LightsIndexed{tris60, lights, n_lights}.sample(r0, r1, r2);
+            ++n_shadow;
             const float V = check_visibility(bvh, surf.p, surf.n, ls.p);
             const f3 brdf = kInvPi * color;
             const float G = geometry_term(surf.p, surf.n, ls.p, ls.n);
@@ -278,6 +283,7 @@ CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh
         else if (EX == 9)
         {
             const Res r = ris_candidates(bvh, LightsIndexed{tris60, lights, n_lights}, surf, opt.ris_count, opt.shadowed, rng);
+            n_shadow += 1u + (opt.shadowed ? (uint32_t)(opt.ris_count > 0 ? opt.ris_count : 0) + 1u : 0u);
             const f3 brdf = kInvPi * color;
             const float G = geometry_term(surf.p, surf.n, r.s.hp, r.s.hn);
             const float V = check_visibility(bvh, surf.p, surf.n, r.s.hp);
@@ -290,13 +296,15 @@ CRT_HD void px_path_trace(const Pix& px, int W, int H, int frame, const Bvh& bvh
         rd = wo;
     }
     write_accum(accum, px.idx, radiance, opt.accumulate);
+    return n_closest | (n_shadow << 16);
 }
 
 // ---- 06_ao_hiprt.cu:35-91, N_Rays as a parameter; returns the RGBA8 pixel
 template <class M>
 CRT_HD uint32_t px_ao(const Pix& px, const crt_raygen& raygen, int W, int H, const Bvh& bvh, const float* tris60,
-                      int n_rays)
+                      int n_rays, uint32_t& ao_rays_traced)
 {
+    ao_rays_traced = 0;
     Pcg rng(0, hash_pcg3(px.xi, px.yi, 42));
     f3 ro, rd;
     primary_ray(raygen, px, W, H, ro, rd);
@@ -310,6 +318,7 @@ CRT_HD uint32_t px_ao(const Pix& px, const crt_raygen& raygen, int W, int H, con
     const f3 t1 = cross(t0, n);
     const f3 ao_ro = ro + rd * h.t + n * 0.0001f;
     int n_visible = 0;
+    ao_rays_traced = (uint32_t)(n_rays > 0 ? n_rays : 0);
     for (int i = 0; i < n_rays; i++)
     {
         const float r0 = rng.next_f();

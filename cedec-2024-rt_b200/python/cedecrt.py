@@ -183,6 +183,8 @@ def _load():
     lib.crt_get_stream.argtypes = [P]
     lib.crt_shadow_rays_traced.restype = C.c_int
     lib.crt_shadow_rays_traced.argtypes = [P, C.POINTER(C.c_ulonglong)]
+    lib.crt_inline_rays_traced.restype = C.c_int
+    lib.crt_inline_rays_traced.argtypes = [P, C.POINTER(C.c_ulonglong)]
     lib.crt_launch_count.restype = C.c_ulonglong
     lib.crt_launch_count.argtypes = [P]
     lib.crt_raygen_lookat.restype = None
@@ -329,6 +331,12 @@ class Runtime:
         """(visibility-reuse rays, resolve rays) traced through the wavefront queue since crt_init (synchronises)"""
         out = (C.c_ulonglong * 2)()
         self._check(self.lib.crt_shadow_rays_traced(self.ctx, out))
+        return int(out[0]), int(out[1])
+
+    def inline_rays_traced(self):
+        """(closest-hit, shadow / AO) rays traced inside the single-kernel examples 06-09 since crt_init"""
+        out = (C.c_ulonglong * 2)()
+        self._check(self.lib.crt_inline_rays_traced(self.ctx, out))
         return int(out[0]), int(out[1])
 
     def sync(self):

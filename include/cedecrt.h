@@ -112,6 +112,10 @@ unsigned long long crt_launch_count(crt_ctx* ctx);
  * visibility-reuse rays (10_restir_di.cu:127-131), out[1] resolve rays (:443-444); waits for the stream.  The fused frame traces fewer than the reference's two per diffuse pixel: the visibility-reuse ray
  * only for candidates that survive the temporal merge, the resolve ray only when it has not been traced before. */
 int crt_shadow_rays_traced(crt_ctx* ctx, unsigned long long out[2]);
+/* rays traced inside the single-kernel examples (crt_ao_06, crt_path_trace_07/08/09) since crt_init — out[0]
+ * closest-hit rays (camera and bounce rays), out[1] shadow / AO rays, counted per path vertex as SURVEY.md section 8d
+ * counts them (08_nee.cu:43,76-77; 09_ris.cu:90-93,112,116-119; 06_ao_hiprt.cu:71-82); waits for the stream */
+int crt_inline_rays_traced(crt_ctx* ctx, unsigned long long out[2]);
 /* TypedBuffer<T>(DEVICE).allocate / dtor / toDevice / toHost (common/typedbuffer.hpp:29-77);
  * memory is uninitialised, as with oroMalloc */
 int crt_malloc(crt_ctx* ctx, size_t bytes, void** out);

@@ -343,8 +343,9 @@ extern "C"
         const Bvh bvh = ((EmuGeom*)gp)->view();
         launch(W, H, [&](Pix p)
                {
-                   pixels[p.idx] = g_math_mode ? px_ao<Math<1>>(p, *rg, W, H, bvh, (const float*)tris, n_rays)
-                                               : px_ao<Math<0>>(p, *rg, W, H, bvh, (const float*)tris, n_rays);
+                   uint32_t ao_rays = 0;
+                   pixels[p.idx] = g_math_mode ? px_ao<Math<1>>(p, *rg, W, H, bvh, (const float*)tris, n_rays, ao_rays)
+                                               : px_ao<Math<0>>(p, *rg, W, H, bvh, (const float*)tris, n_rays, ao_rays);
                });
         return 0;
     }
