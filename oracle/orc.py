@@ -76,11 +76,19 @@ def make_options(**kw):
     return o
 
 
-def fnv1a64(a):
-    """FNV-1a-64 over the bytes of an array (the hash SURVEY.md section 2.3/4 quotes goldens in)."""
+SURVEY_FNV_BASIS = 1469598103934665603  # the offset basis of the survey's probe: the standard one minus its last digit
+
+
+def fnv1a64(a, basis=None):
+    """FNV-1a-64 over the bytes of an array.  basis=SURVEY_FNV_BASIS reproduces the goldens SURVEY.md sections 2.3 / 4
+    quote (their probe started from a truncated offset basis); the default is the standard 0xcbf29ce484222325."""
     data = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
     lib = _fnv_lib()
-    return "%016x" % lib.orc_fnv1a64(data.ctypes.data_as(C.c_void_p), C.c_size_t(data.size))
+    if basis is None:
+        return "%016x" % lib.orc_fnv1a64(data.ctypes.data_as(C.c_void_p), C.c_size_t(data.size))
+    lib.orc_fnv1a64_from.restype = C.c_uint64
+    lib.orc_fnv1a64_from.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
+    return "%016x" % lib.orc_fnv1a64_from(data.ctypes.data_as(C.c_void_p), C.c_size_t(data.size), C.c_uint64(basis))
 
 
 _FNV = None

@@ -627,6 +627,15 @@ extern "C"
         for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ULL;
         return h;
     }
+    // the same walk from another offset basis.  SURVEY.md sections 2.3 / 4 quote their goldens from a probe whose
+    // basis was 1469598103934665603 — the standard basis 14695981039346656037 with its last digit dropped — so
+    // checking those values needs that start value (tests/test_oracle_pinning.py: SURVEY_FNV_BASIS).
+    uint64_t orc_fnv1a64_from(const uint8_t* p, size_t n, uint64_t basis)
+    {
+        uint64_t h = basis;
+        for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ULL;
+        return h;
+    }
 
     uint32_t orc_hash_pcg3(uint32_t x, uint32_t y, uint32_t z) { return hash_pcg3(x, y, z); }
     uint32_t orc_hash_pcg4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return hash_pcg4(x, y, z, w); }

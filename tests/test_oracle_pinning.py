@@ -45,6 +45,49 @@ def test_scene_goldens_shape():
     assert len(cb) == 36 and len(ao) == 3034
     assert len(orc.light_indices(cb)) == 2 and len(orc.light_indices(ao)) == 0
     assert orc.fnv1a64(cb) == "fedadd381237eb3b" and orc.fnv1a64(ao) == "a2d990e76bb6ff22"
+    # SURVEY.md section 2.3 quotes FNV-1a-64 values computed from a truncated offset basis (orc.SURVEY_FNV_BASIS):
+    # with that start value the loader goldens of the survey are reproduced exactly
+    B = orc.SURVEY_FNV_BASIS
+    assert orc.fnv1a64(cb, B) == "cc18ef135fe511b9" and orc.fnv1a64(ao, B) == "df1ba0d5b8625ddc"
+
+
+# primary-visibility goldens of the reference's own raycast kernel + core.hpp:91 triangle test on the
+# real scenes at the reference cameras, 1920x1080: (sky, emissive, diffuse) pixel counts and FNV-1a-64 (survey basis) of
+# the int32 primitive-id image in pixel_idx order.  BASELINE configs 2, 3 and 4/5 (untiled) respectively.
+SURVEY_PRIMARY = {
+    "blocks_ao": (((8.0, 8.0, 8.0), (0.0, 0.0, 0.0)), (547781, 0, 1525819), "6036eeb91fb634ed", "df1ba0d5b8625ddc"),
+    "blocks_pt": (((5.983407, 13.970583, -28.553869), (-5.354514, 4.815835, -2.047728)), (138584, 0, 1935016),
+                  "7d6a1cbc62121ca3", "868ff28a3e06c60f"),
+    "blocks_restir": (((-0.579885, 22.194597, -6.567105), (5.224952, 20.847435, 1.431192)), (197500, 272518, 1603582),
+                      "14de7a5a6a1f96ec", "9d9d4b4ced5814de"),
+}
+
+
+def pixel_classes(idx, tris):
+    em = (tris["emissive"] > 0).any(1)
+    sky = idx < 0
+    emi = np.zeros(len(idx), bool)
+    emi[~sky] = em[idx[~sky]]
+    return int(sky.sum()), int(emi.sum()), int((~sky & ~emi).sum())
+
+
+@pytest.mark.parametrize("scene", sorted(SURVEY_PRIMARY))
+def test_primary_visibility_matches_the_survey_goldens(port, scene):
+    """the oracle's raycast (10_restir_di.cu:9-34 restated + the reference triangle test inside oracle/cpu_bvh.h) on the
+    staged scene caches reproduces the survey's goldens bit for bit: scene bytes, pixel classes, primitive-id image"""
+    import stage_assets
+
+    if not stage_assets.have_scene(scene):
+        pytest.skip("scene cache assets/%s.tri.xz not staged" % scene)
+    cam, classes, prim_hash, scene_hash = SURVEY_PRIMARY[scene]
+    tris = stage_assets.load_scene(scene)
+    assert orc.fnv1a64(tris, orc.SURVEY_FNV_BASIS) == scene_hash
+    W, H = 1920, 1080
+    g = port.geom_build(tris)
+    vis = port.raycast(W, H, g, tris, port.lookat(*cam, W, H))
+    port.geom_free(g)
+    assert pixel_classes(vis["index"], tris) == classes
+    assert orc.fnv1a64(vis["index"], orc.SURVEY_FNV_BASIS) == prim_hash
 
 
 def test_restir_chain_matches_reference_golden(gxx_port):
