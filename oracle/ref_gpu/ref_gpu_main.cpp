@@ -39,9 +39,10 @@ static double now_s()
 
 int main(int argc, char** argv)
 {
-    std::string base = "./", tri_path, dump_vis;
+    std::string base = "./", tri_path, dump_vis, dump_candidates;
     int width = 3840, height = 2160, frames = 8, warmup = 3, nx = 1, nz = 1;
     float pitch_x = 130.0f, pitch_z = 82.0f;
+    float3 cameraOrig{-0.579885f, 22.194597f, -6.567105f}, cameraLookat{5.224952f, 20.847435f, 1.431192f};
     for (int i = 1; i < argc; i++)
     {
         auto is = [&](const char* k) { return !strcmp(argv[i], k) && i + 1 < argc; };
@@ -54,6 +55,11 @@ int main(int argc, char** argv)
         else if (is("--tiles-x")) nx = atoi(argv[++i]);
         else if (is("--tiles-z")) nz = atoi(argv[++i]);
         else if (is("--dump-vis")) dump_vis = argv[++i];
+        // Reservoir[] exactly as generate_candidate leaves it on frame 1 (10_restir_di.cu:36-135), before any other kernel
+        // touches it: pins the order in which NVRTC evaluates the uniformf() arguments of sample_light (:88-90)
+        else if (is("--dump-candidates")) dump_candidates = argv[++i];
+        else if (!strcmp(argv[i], "--eye") && i + 3 < argc) { cameraOrig.x = (float)atof(argv[++i]); cameraOrig.y = (float)atof(argv[++i]); cameraOrig.z = (float)atof(argv[++i]); }
+        else if (!strcmp(argv[i], "--lookat") && i + 3 < argc) { cameraLookat.x = (float)atof(argv[++i]); cameraLookat.y = (float)atof(argv[++i]); cameraLookat.z = (float)atof(argv[++i]); }
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (base.back() != '/') base += '/';
@@ -164,7 +170,6 @@ int main(int argc, char** argv)
     options.accumulate = true;
     options.use_temporal_resampling = true;
     options.use_spatial_resampling = true;
-    const float3 cameraOrig{-0.579885f, 22.194597f, -6.567105f}, cameraLookat{5.224952f, 20.847435f, 1.431192f};
     const int grid = ceiling_div(width * height, 256);
 
     shader.launch("clear", ShaderArgument().ptr(&accumulation_buffer).value(width).value(height), grid, 1, 1, 256, 1, 1,
@@ -187,6 +192,14 @@ int main(int argc, char** argv)
                       ShaderArgument().value(width).value(height).value(frame).value(geom).ptr(&triangle_buffer).ptr(&visibility_buffer)
                           .value(cameraOrig).ptr(&light_buffer).value(options).ptr(&reservoir_buffer0),
                       grid, 1, 1, 256, 1, 1, stream);
+        if (it == 0 && !dump_candidates.empty())
+        {
+            oroStreamSynchronize(stream);
+            TypedBuffer<Reservoir> cand = reservoir_buffer0.toHost();
+            TypedBuffer<Visibility> v0 = visibility_buffer.toHost();
+            FILE* f = fopen(dump_candidates.c_str(), "wb");
+            if (f) { fwrite(cand.data(), sizeof(Reservoir), n_px, f); fwrite(v0.data(), sizeof(Visibility), n_px, f); fclose(f); }
+        }
         shader.launch("temporal_resampling",
                       ShaderArgument().value(width).value(height).value(frame).value(geom).ptr(&triangle_buffer).ptr(&visibility_buffer)
                           .value(cameraOrig).value(options).ptr(&temporal_reservoir_buffer).ptr(&reservoir_buffer0),
