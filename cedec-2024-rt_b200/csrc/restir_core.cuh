@@ -45,7 +45,7 @@ CRT_HD void shoot(const RayGen& rg, float u, float v, f3& ro, f3& rd)
 CRT_HD float check_visibility(const Bvh& bvh, f3 p0, f3 n0, f3 p1)
 {
     Hit h;
-    return trace<true>(bvh, p0 + 0.001f * n0, p1 - p0, 0.0f, 0.99f, h) ? 0.0f : 1.0f;
+    return trace<true, true>(bvh, p0 + 0.001f * n0, p1 - p0, 0.0f, 0.99f, h) ? 0.0f : 1.0f;  // towards a light: far end first
 }
 
 // ---- surfaces (core.hpp:188-207 and 152-165)

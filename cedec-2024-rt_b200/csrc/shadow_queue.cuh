@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                         const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
                         pix = __float_as_uint(w0.w);
                         ray_idx = my;
-                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z});
+                        // visibility-reuse rays aim at freshly sampled lights: 93 % are occluded, mostly next to the light, so
+                        // their walk starts at the far end (bvh.cuh: setup_ray); resolve rays aim at samples that survived
+                        // the resampling — three quarters are clear, and for the rest the near end finds the blocker sooner
+                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z}, EPI != kEpiResolve);
                         walk_begin(w, r);
                         active = true;
                     }

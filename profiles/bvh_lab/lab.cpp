@@ -349,6 +349,60 @@ int main(int argc, char** argv)
         printf("   pre-reject by plane side %.1f%%, then by bounding sphere at the crossing %.1f%% (of all failed tests)\n", 100.0 * rej_plane / tests, 100.0 * rej_sphere / tests);
         for (auto& kv : by_leaf) printf("   leaf size %d, own box %s: %.2f per ray\n", kv.first / 2, kv.first & 1 ? "hit " : "miss", (double)kv.second / rays_n);
     }
+    // any-hit child order: front-to-back (the walk's) against back-to-front (the octant of the reversed direction)
+    {
+        auto walk_any = [&](const RayRec& r, bool reversed, unsigned& nodes, unsigned& tris)
+        {
+            RaySetup rsu = setup_ray(r.o, r.d);
+            if (reversed) rsu.octinv ^= 7u;
+            Walk w;
+            walk_begin(w, rsu);
+            nodes = tris = 0;
+            for (;;)
+            {
+                if ((w.ng_mask >> 24) == 0)
+                {
+                    if (w.sp == 0) return false;
+                    --w.sp;
+                    w.ng_base = w.stack_base[w.sp];
+                    w.ng_mask = w.stack_mask[w.sp];
+                }
+                const int bit = 31 - clz32(w.ng_mask);
+                w.ng_mask &= ~(1u << bit);
+                const uint32_t slot = (uint32_t)(bit - 24) ^ rsu.octinv;
+                const uint32_t node_idx = w.ng_base + (uint32_t)popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
+                if (w.ng_mask >> 24) { w.stack_base[w.sp] = w.ng_base; w.stack_mask[w.sp] = w.ng_mask; ++w.sp; }
+                uint32_t imask;
+                const uint32_t hits = intersect_node(bvh, node_idx, rsu, 0.0f, 0.99f, w.ng_base, w.tri_base, imask);
+                nodes++;
+                w.ng_mask = (hits & 0xff000000u) | imask;
+                uint32_t tm = hits & 0x00ffffffu;
+                while (tm)
+                {
+                    const int i = 31 - clz32(tm & (0u - tm));
+                    tm &= tm - 1u;
+                    Hit h; h.prim = -1; h.t = 0.99f; h.u = h.v = 0;
+                    tris++;
+                    if (intersect_wide_tri(bvh.tris + w.tri_base + i, rsu, 0.0f, h)) return true;
+                }
+            }
+        };
+        for (int cls = 0; cls < 2; cls++)
+        {
+            const std::vector<RayRec>& rays = cls ? rs : vr;
+            double n0 = 0, t0 = 0, n1 = 0, t1 = 0;
+            size_t cnt = 0;
+            for (const RayRec& r : rays)
+            {
+                unsigned a, b, c, d;
+                const bool h0 = walk_any(r, false, a, b), h1 = walk_any(r, true, c, d);
+                if (h0 != h1) printf("ORDER CHANGES RESULT?!\n");
+                n0 += a; t0 += b; n1 += c; t1 += d; cnt++;
+            }
+            printf("any-hit order, %s rays: front-to-back nodes %.2f tris %.2f | back-to-front nodes %.2f tris %.2f\n", cls ? "resolve" : "visibility-reuse",
+                   n0 / cnt, t0 / cnt, n1 / cnt, t1 / cnt);
+        }
+    }
     // dump rays for tree experiments
     if (const char* dump = getenv("LAB_DUMP"))
     {

@@ -244,6 +244,12 @@ extern "C"
         Hit h;
         return trace<true>(((EmuGeom*)gp)->view(), v3(o), v3(d), tmin, tmax, h) ? 1 : 0;
     }
+    // the same question with the children nearest to the ray's end visited first (bvh.cuh: setup_ray far_first)
+    int emu_any_hit_far_first(void* gp, const float* o, const float* d, float tmin, float tmax)
+    {
+        Hit h;
+        return trace<true, true>(((EmuGeom*)gp)->view(), v3(o), v3(d), tmin, tmax, h) ? 1 : 0;
+    }
     void orc_clear(crt_float4* buf, int W, int H)
     {
         launch(W, H, [&](Pix p) { buf[p.idx] = {0, 0, 0, 0}; });
@@ -377,7 +383,7 @@ extern "C"
                    if (d.want)
                    {
                        Hit h;
-                       if (!trace<true>(bvh, d.org, d.dir, 0.0f, 0.99f, h)) *T.mword(p.idx) |= kVisBit;
+                       if (!trace<true, true>(bvh, d.org, d.dir, 0.0f, 0.99f, h)) *T.mword(p.idx) |= kVisBit;  // k_trace_shadow_queue<2>
                    }
                });
         SoaStore in = T, out = A;

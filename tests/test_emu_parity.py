@@ -120,6 +120,7 @@ def test_wide_bvh_equals_brute_force(emu, port):
     lib = port.lib
     lib.orc_closest_hit_brute.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
     emu.lib.emu_any_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+    emu.lib.emu_any_hit_far_first.argtypes = emu.lib.emu_any_hit.argtypes
     rng = np.random.default_rng(7)
     hits = 0
     for i in range(600):
@@ -136,6 +137,8 @@ def test_wide_bvh_equals_brute_force(emu, port):
                                          tuv2.ctypes.data)
         assert idx == idx2 and (idx < 0 or same(tuv, tuv2)), (i, o, d)
         assert emu.lib.emu_any_hit(g, o.ctypes.data, d.ctypes.data, 0.0, tmax) == (1 if idx2 >= 0 else 0)
+        # far end first (shadow rays towards lights): another visiting order, the same answer
+        assert emu.lib.emu_any_hit_far_first(g, o.ctypes.data, d.ctypes.data, 0.0, tmax) == (1 if idx2 >= 0 else 0)
         # the same walk with triangle groups postponed whenever the walk allows it (the divergence control of
         # the CUDA path; any visiting order must give the same closest hit)
         emu.lib.emu_set_postpone(1)
