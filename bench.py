@@ -356,7 +356,7 @@ def run_cuda(args):
         sub = 1
     r = None
     if sub > 1:
-        r = SlabGroup(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, sub=sub)
+        r = SlabGroup(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, sub=sub, overlap=bool(args.overlap))
         # pre-flight: two frames; if any slab's wait for a neighbour timed out anywhere, every rank falls back to one slab
         for _ in range(2):
             r.frame()
@@ -379,7 +379,8 @@ def run_cuda(args):
             r.reset_history()
             torch.cuda.synchronize()
     if r is None:
-        r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"))
+        r = SlabRenderer(torch, dist if world > 1 else None, rank, world, tris, cam, W, H, fused=fused, p2p=(args.halo == "p2p"),
+                         overlap=bool(args.overlap))
     import cedecrt
     math_mode = {"reference": cedecrt.MATH_REFERENCE, "libdevice": cedecrt.MATH_LIBDEVICE, "fast": cedecrt.MATH_FAST,
                  "exact": cedecrt.MATH_EXACT}[args.math]
@@ -564,6 +565,8 @@ def run_cuda(args):
                        "camera": "10_restir_di.cpp:188-189",
                        "mode": "fused frame (crt_restir_frame_begin / spatial_pass / frame_end, SoA reservoirs)" if fused
                                else "per-kernel launch list (drop-in, AoS reservoirs)",
+                       "frame_overlap": ("tail of frame f (resolve rays, tone mapping) on a second stream beside the head of frame f+1"
+                                         if getattr(r.slabs[0], "overlap", False) else "none: frames strictly serial"),
                        "slab_edges": r.edges,
                        "partition": "%d row slab(s)%s, halo %d rows, %s" % (
                            world * sub, " (%d per GPU, one CUDA stream each)" % sub if sub > 1 else "", HALO_ROWS, "halo rows stored directly into the neighbours' buffers over NVLink "
@@ -965,6 +968,9 @@ def main():
     ap.add_argument("--math", default="reference", choices=["reference", "libdevice", "fast", "exact"],
                     help="arithmetic of the reservoir kernels (include/cedecrt.h: CRT_MATH_*); reference = nvcc/NVRTC defaults, "
                          "the reference's own GPU arithmetic")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
+                    help="1 (default): the frame's tail (resolve rays + tone mapping) runs on a second stream beside the next "
+                         "frame's raycast / candidate kernels (crt_set_frame_overlap); 0: strictly serial frames like the reference")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference Orochi/HIPRT comparator run (N = 1, 4K)")
     ap.add_argument("--no-frame-hash", action="store_true", help="skip the exact-mode frame fingerprint")
     ap.add_argument("--config", default="10", choices=["10", "06", "08", "09"],

@@ -59,6 +59,15 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
     if (!ctx) return CRT_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->tail_stream)
+    {
+        cudaStreamSynchronize(ctx->tail_stream);
+        cudaStreamDestroy(ctx->tail_stream);
+        cudaEventDestroy(ctx->ev_head);
+        cudaEventDestroy(ctx->ev_tail);
+    }
+    if (ctx->queue2_rays) cudaFree(ctx->queue2_rays);
+    if (ctx->queue2_counters) cudaFree(ctx->queue2_counters);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
     if (ctx->queue_rays) cudaFree(ctx->queue_rays);
@@ -93,9 +102,32 @@ extern "C" int crt_set_row_range(crt_ctx* ctx, int y_begin, int y_end)
     return CRT_OK;
 }
 
+extern "C" int crt_set_frame_overlap(crt_ctx* ctx, int on)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
+    if (on && !ctx->tail_stream)
+    {
+        CRT_CUDA(cudaSetDevice(ctx->device));
+        CRT_CUDA(cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking));
+        CRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_head, cudaEventDisableTiming));
+        CRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming));
+    }
+    ctx->overlap = on ? 1 : 0;
+    return CRT_OK;
+}
+extern "C" int crt_frame_join(crt_ctx* ctx)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
+    return CRT_OK;
+}
+extern "C" void* crt_get_tail_stream(crt_ctx* ctx) { return ctx ? (void*)ctx->tail_stream : nullptr; }
+
 extern "C" int crt_set_stream(crt_ctx* ctx, void* cuda_stream)
 {
     CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return CRT_OK;
 }
@@ -104,6 +136,7 @@ extern "C" unsigned long long crt_launch_count(crt_ctx* ctx) { return ctx ? ctx-
 extern "C" int crt_shadow_rays_traced(crt_ctx* ctx, unsigned long long out[2])
 {
     CRT_REQUIRE(ctx && out, "null argument");
+    CRT_JOIN_TAIL(ctx);
     out[0] = out[1] = 0;
     if (!ctx->queue_counters) return CRT_OK;
     CRT_CUDA(cudaMemcpyAsync(out, ctx->queue_counters + 2, 2 * sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
@@ -127,12 +160,14 @@ extern "C" int crt_free(crt_ctx* ctx, void* p)
 extern "C" int crt_memset(crt_ctx* ctx, void* p, int byte, size_t bytes)
 {
     CRT_REQUIRE(ctx && (p || !bytes), "null argument");
+    CRT_JOIN_TAIL(ctx);
     if (bytes) CRT_CUDA(cudaMemsetAsync(p, byte, bytes, ctx->stream));
     return CRT_OK;
 }
 extern "C" int crt_memcpy_h2d(crt_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     CRT_REQUIRE(ctx && ((dst && src) || !bytes), "null argument");
+    CRT_JOIN_TAIL(ctx);
     if (!bytes) return CRT_OK;
     CRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CRT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -141,6 +176,7 @@ extern "C" int crt_memcpy_h2d(crt_ctx* ctx, void* dst, const void* src, size_t b
 extern "C" int crt_memcpy_d2h(crt_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     CRT_REQUIRE(ctx && ((dst && src) || !bytes), "null argument");
+    CRT_JOIN_TAIL(ctx);
     if (!bytes) return CRT_OK;
     CRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CRT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -149,24 +185,28 @@ extern "C" int crt_memcpy_d2h(crt_ctx* ctx, void* dst, const void* src, size_t b
 extern "C" int crt_memcpy_d2h_async(crt_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     CRT_REQUIRE(ctx && ((dst && src) || !bytes), "null argument");
+    CRT_JOIN_TAIL(ctx);
     if (bytes) CRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return CRT_OK;
 }
 extern "C" int crt_sync(crt_ctx* ctx)
 {
     CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
     CRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRT_OK;
 }
 extern "C" int crt_timer_start(crt_ctx* ctx)
 {
     CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
     CRT_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
     return CRT_OK;
 }
 extern "C" int crt_timer_stop_ms(crt_ctx* ctx, float* ms)
 {
     CRT_REQUIRE(ctx && ms, "null argument");
+    CRT_JOIN_TAIL(ctx);
     CRT_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
     CRT_CUDA(cudaEventSynchronize(ctx->ev_stop));
     CRT_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
@@ -179,6 +219,7 @@ extern "C" int crt_timer_stop_ms(crt_ctx* ctx, float* ms)
 extern "C" int crt_profile_begin(crt_ctx* ctx)
 {
     CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
     if (!ctx->prof_start) CRT_CUDA(cudaEventCreate(&ctx->prof_start));
     for (auto& m : ctx->prof_marks) ctx->prof_pool.push_back(m.second);
     ctx->prof_marks.clear();
@@ -189,6 +230,7 @@ extern "C" int crt_profile_begin(crt_ctx* ctx)
 extern "C" int crt_profile_end(crt_ctx* ctx, char* names, size_t names_cap, float* ms, int ms_cap, int* count)
 {
     CRT_REQUIRE(ctx && names && ms && count, "null argument");
+    CRT_JOIN_TAIL(ctx);
     CRT_REQUIRE(ctx->profiling, "crt_profile_begin was not called");
     ctx->profiling = false;
     CRT_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -235,6 +235,26 @@ CRT_HD uint32_t intersect_node(const Bvh& bvh, uint32_t node_idx, const RaySetup
     }
     uint32_t hits = 0;
     const uint32_t one = bvh.f32_one;
+#if defined(__CUDA_ARCH__) && !defined(CRT_NODE_NO_FFMA2)
+    // sm_100 packed FP32: one FFMA2 evaluates the same plane of two slots (fma.rn.f32x2), halving the issue slots of
+    // the 48 plane evaluations; the results are the very same fmaf values.  Measured (profiles/r2/tuning.txt, 4K
+    // config 5): raycast 1.98 -> 1.85 ms, visibility-reuse rays 1.81 -> 1.73, resolve rays 3.34 -> 3.26
+#define CRT_PLANE2(WORD, K, A, O) __ffma2_rn(make_float2(byte_to_unit_float<K>(WORD, one), byte_to_unit_float<K + 1>(WORD, one)), make_float2(A, A), make_float2(O, O))
+#define CRT_SLOT_BITS(W, K) (((child_bits[W] >> (8 * (K))) & 0xffu) << ((bit_index[W] >> (8 * (K))) & 0xffu))
+#define CRT_SLOT2(W, K)                                                                                                     \
+    {                                                                                                                       \
+        const float2 nx2 = CRT_PLANE2(nearx[W], K, ax, ox), ny2 = CRT_PLANE2(neary[W], K, ay, oy), nz2 = CRT_PLANE2(nearz[W], K, az, oz); \
+        const float2 fx2 = CRT_PLANE2(farx[W], K, ax, ox), fy2 = CRT_PLANE2(fary[W], K, ay, oy), fz2 = CRT_PLANE2(farz[W], K, az, oz);    \
+        const float t0a = fmaxf(fmaxf(nx2.x, ny2.x), fmaxf(nz2.x, tmin)), t1a = fminf(fminf(fx2.x, fy2.x), fminf(fz2.x, tmax));  \
+        const float t0b = fmaxf(fmaxf(nx2.y, ny2.y), fmaxf(nz2.y, tmin)), t1b = fminf(fminf(fx2.y, fy2.y), fminf(fz2.y, tmax));  \
+        hits |= t0a <= t1a ? CRT_SLOT_BITS(W, K) : 0u;                                                                      \
+        hits |= t0b <= t1b ? CRT_SLOT_BITS(W, K + 1) : 0u;                                                                  \
+    }
+    CRT_SLOT2(0, 0) CRT_SLOT2(0, 2) CRT_SLOT2(1, 0) CRT_SLOT2(1, 2)
+#undef CRT_SLOT2
+#undef CRT_SLOT_BITS
+#undef CRT_PLANE2
+#else
 #define CRT_SLOT(W, K)                                                                                                      \
     {                                                                                                                       \
         const float t0 = fmaxf(fmaxf(fmaf(byte_to_unit_float<K>(nearx[W], one), ax, ox),                                    \
@@ -248,6 +268,7 @@ CRT_HD uint32_t intersect_node(const Bvh& bvh, uint32_t node_idx, const RaySetup
     }
     CRT_SLOT(0, 0) CRT_SLOT(0, 1) CRT_SLOT(0, 2) CRT_SLOT(0, 3) CRT_SLOT(1, 0) CRT_SLOT(1, 1) CRT_SLOT(1, 2) CRT_SLOT(1, 3)
 #undef CRT_SLOT
+#endif
     child_base = n1.x;
     tri_base = n1.y;
     imask_out = imask;
@@ -293,9 +314,19 @@ extern int g_emu_postpone;
 #define CRT_LANES_WALKING() 32
 #endif
 
+// The stack lives in local memory (dynamic indexing); everything else of the walk's state is meant for registers, so
+// the two are separate objects: as members of one struct the scalars were written back to local memory after every
+// update (23 STL + 10 LDL per node step in k_trace_shadow_queue, profiles/r1).  One 64-bit entry per push / pop.
+struct WalkEntry
+{
+    uint32_t base, mask;
+};
+struct alignas(8) WalkStack
+{
+    WalkEntry e[kStackSize];
+};
 struct Walk
 {
-    uint32_t stack_base[kStackSize], stack_mask[kStackSize];
     int sp;
     uint32_t ng_base, ng_mask;  // node group: inner-child hits in bits 24..31 (by priority), imask in bits 0..7
     uint32_t tri_base, tmask;   // triangle group: hit triangles of the last node's leaf children
@@ -313,7 +344,7 @@ enum { kWalkContinue = 0, kWalkDone = 1, kWalkHitAny = 2 };
 
 // lanes_walking: number of lanes of the warp that entered this iteration (read at a converged point)
 template <bool ANY, bool POSTPONE>
-CRT_HD int walk_step(const Bvh& bvh, Walk& w, const RaySetup& r, float tmin, Hit& hit, int lanes_walking)
+CRT_HD int walk_step(const Bvh& bvh, Walk& w, WalkStack& st, const RaySetup& r, float tmin, Hit& hit, int lanes_walking)
 {
     // ---- node work: at most one node step
     if (w.tmask == 0)
@@ -322,7 +353,8 @@ CRT_HD int walk_step(const Bvh& bvh, Walk& w, const RaySetup& r, float tmin, Hit
         {
             if (w.sp == 0) return kWalkDone;
             --w.sp;
-            const uint32_t b = w.stack_base[w.sp], m = w.stack_mask[w.sp];
+            const WalkEntry top = st.e[w.sp];
+            const uint32_t b = top.base, m = top.mask;
             if (m >> 24)
             {
                 w.ng_base = b;
@@ -342,8 +374,7 @@ CRT_HD int walk_step(const Bvh& bvh, Walk& w, const RaySetup& r, float tmin, Hit
             const uint32_t node_idx = w.ng_base + (uint32_t)popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
             if (w.ng_mask >> 24)
             {
-                w.stack_base[w.sp] = w.ng_base;
-                w.stack_mask[w.sp] = w.ng_mask;
+                st.e[w.sp] = WalkEntry{w.ng_base, w.ng_mask};
                 ++w.sp;
             }
             uint32_t imask;
@@ -354,12 +385,27 @@ CRT_HD int walk_step(const Bvh& bvh, Walk& w, const RaySetup& r, float tmin, Hit
     }
     // ---- triangle work
     const WideTri* tp = bvh.tris + w.tri_base;
+#if defined(__CUDA_ARCH__) && defined(CRT_POSTPONE_BALLOT)
+    // experiment: decide once per step, from a ballot at the point where the node work has rejoined, how many of the
+    // warp's walking lanes own triangles — instead of counting the lanes that happen to execute the loop head together
+    const unsigned walking_now = __activemask();
+    const int lanes_with_tris = __popc(__ballot_sync(walking_now, w.tmask != 0u));
+    if (POSTPONE && w.tmask && (w.ng_mask >> 24) != 0 && (float)lanes_with_tris < bvh.postpone_ratio * (float)__popc(walking_now))
+    {
+        st.e[w.sp] = WalkEntry{w.tri_base, w.tmask};
+        ++w.sp;
+        w.tmask = 0;
+    }
+#endif
     while (w.tmask)
     {
+#if !defined(CRT_POSTPONE_BALLOT)
         if (POSTPONE && (w.ng_mask >> 24) != 0 && (float)CRT_LANES_HERE() < bvh.postpone_ratio * (float)lanes_walking)
+#else
+        if (false)
+#endif
         {
-            w.stack_base[w.sp] = w.tri_base;
-            w.stack_mask[w.sp] = w.tmask;
+            st.e[w.sp] = WalkEntry{w.tri_base, w.tmask};
             ++w.sp;
             w.tmask = 0;
             break;
@@ -382,13 +428,29 @@ CRT_HD bool trace(const Bvh& bvh, f3 ro, f3 rd, float tmin, float tmax, Hit& hit
     hit.t = tmax;
     hit.u = hit.v = 0.0f;
     const RaySetup r = setup_ray(ro, rd, FAR_FIRST);
+#if !defined(CRT_WALK_SPLIT_OBJECTS)
+    // Stack and scalars as members of one object: the compiler then keeps the scalars in local memory too — more
+    // instructions, and yet faster here: this per-thread walk's divergence control (triangle postponing by
+    // __activemask() counts) depends on where the compiler lets the lanes rejoin, and with register-resident scalars it
+    // rejoined less (k_raycast 26.6 -> 24.7 lanes per instruction, 1.98 -> 2.11 ms; 08_nee 3.9 -> 4.6 ms per frame:
+    // profiles/r2/tuning.txt).  The persistent shadow-ray kernel has no such dependence and uses the split objects.
+    struct
+    {
+        WalkStack stack;
+        Walk w;
+    } both;
+    Walk& w = both.w;
+    WalkStack& stack = both.stack;
+#else
     Walk w;
+    WalkStack stack;
+#endif
     walk_begin(w, r);
     for (;;)
     {
         const int lanes = CRT_LANES_WALKING();
-        const int st = walk_step<ANY, true>(bvh, w, r, tmin, hit, lanes);
-        if (st != kWalkContinue) break;
+        const int state = walk_step<ANY, true>(bvh, w, stack, r, tmin, hit, lanes);
+        if (state != kWalkContinue) break;
     }
     return hit.prim >= 0;
 }

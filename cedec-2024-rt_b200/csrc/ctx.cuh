@@ -24,6 +24,15 @@ struct crt_ctx
     unsigned* queue_counters = nullptr;
     size_t queue_capacity = 0;
     unsigned long long* inline_rays = nullptr;  // {closest-hit, shadow / AO} rays traced by the single-kernel examples 06-09
+    // frame overlap (crt_set_frame_overlap): the tail of the fused frame — the resolve rays and tone mapping — runs on a
+    // second stream, so that the next frame's raycast and candidate kernels fill the tail's drain (and vice versa)
+    int overlap = 0;
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
+    bool tail_pending = false;  // a tail has been issued that ctx->stream has not been ordered after yet
+    void* queue2_rays = nullptr;  // the resolve rays' own queue while frames overlap (the next frame's visibility-reuse rays use the first)
+    unsigned* queue2_counters = nullptr;
+    size_t queue2_capacity = 0;
     int wavefront = 1;  // 0: trace shadow rays inside the per-pixel kernels (CRT_WAVEFRONT=0)
     int light_table = 1;  // 0: sample lights through lights[] -> triangles[] like the reference (CRT_LIGHT_TABLE=0)
     // fused frame (kernels_fast.cu): G-buffer + pixel-class plane, 25 bytes per pixel, grown on demand
@@ -95,7 +104,7 @@ void set_error(const char* fmt, ...);
         }                                               \
     } while (0)
 
-inline int check_launch(crt_ctx* ctx, const char* what)
+inline int check_launch(crt_ctx* ctx, const char* what, cudaStream_t on = nullptr)
 {
     ctx->launches++;
     if (ctx->profiling)
@@ -107,7 +116,7 @@ inline int check_launch(crt_ctx* ctx, const char* what)
             ctx->prof_pool.pop_back();
         }
         else cudaEventCreate(&ev);
-        cudaEventRecord(ev, ctx->stream);
+        cudaEventRecord(ev, on ? on : ctx->stream);
         ctx->prof_marks.emplace_back(what, ev);
     }
     cudaError_t e = cudaGetLastError();
@@ -118,6 +127,23 @@ inline int check_launch(crt_ctx* ctx, const char* what)
     }
     return CRT_OK;
 }
+
+// order everything issued to ctx->stream from now on after the frame tail in flight (no-op without overlap)
+inline int join_tail(crt_ctx* ctx)
+{
+    if (ctx->tail_pending)
+    {
+        CRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0));
+        ctx->tail_pending = false;
+    }
+    return CRT_OK;
+}
+#define CRT_JOIN_TAIL(ctx)                        \
+    do                                            \
+    {                                             \
+        const int rc__ = crt::join_tail(ctx);     \
+        if (rc__ != CRT_OK) return rc__;          \
+    } while (0)
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 }  // namespace crt

@@ -267,6 +267,7 @@ extern "C" int crt_resolve(crt_ctx* ctx, crt_buffer accumulation, int W, int H, 
     CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
     CRT_CHECK_BUF(reservoirs, (size_t)W * H, "reservoir");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
+    CRT_JOIN_TAIL(ctx);
     const Rows rows = rows_of(ctx, H);
     crt_float4* accum = (crt_float4*)accumulation.data;
     ShadowQueue q{nullptr, nullptr, nullptr, 0};
@@ -292,6 +293,7 @@ extern "C" int crt_clear(crt_ctx* ctx, crt_buffer buffer, int W, int H)
     CRT_REQUIRE(ctx, "null context");
     CRT_CHECK_IMAGE(W, H);
     CRT_CHECK_BUF(buffer, (size_t)W * H, "accumulation");
+    CRT_JOIN_TAIL(ctx);
     const Rows r = rows_of(ctx, H);
     const size_t n = (size_t)(r.y1 - r.y0) * W, first = (size_t)(H - r.y1) * W;
     if (n == 0) return CRT_OK;
@@ -299,7 +301,9 @@ extern "C" int crt_clear(crt_ctx* ctx, crt_buffer buffer, int W, int H)
     return check_launch(ctx, "clear");
 }
 
-extern "C" int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accumulation, int W, int H)
+namespace crt
+{
+int tone_mapping_on(crt_ctx* ctx, cudaStream_t st, crt_buffer pixels, crt_buffer accumulation, int W, int H)
 {
     CRT_REQUIRE(ctx, "null context");
     CRT_CHECK_IMAGE(W, H);
@@ -309,9 +313,16 @@ extern "C" int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accu
     const size_t n = (size_t)(r.y1 - r.y0) * W, first = (size_t)(H - r.y1) * W;
     if (n == 0) return CRT_OK;
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_tone_mapping<1> : k_tone_mapping<0>;
-    k<<<sweep_blocks(ctx, n), 256, 0, ctx->stream>>>(n, (uint32_t*)pixels.data + first,
-                                                    (const float4*)accumulation.data + first);
-    return check_launch(ctx, "tone_mapping");
+    k<<<sweep_blocks(ctx, n), 256, 0, st>>>(n, (uint32_t*)pixels.data + first, (const float4*)accumulation.data + first);
+    return check_launch(ctx, "tone_mapping", st);
+}
+}  // namespace crt
+
+extern "C" int crt_tone_mapping(crt_ctx* ctx, crt_buffer pixels, crt_buffer accumulation, int W, int H)
+{
+    CRT_REQUIRE(ctx, "null context");
+    CRT_JOIN_TAIL(ctx);
+    return tone_mapping_on(ctx, ctx->stream, pixels, accumulation, W, H);
 }
 
 // two 64-bit device counters per context: closest-hit and shadow / AO rays traced by the single-kernel examples
@@ -344,6 +355,7 @@ static int path_trace(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, 
     CRT_CHECK_BUF(accumulation, (size_t)W * H, "accumulation");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(EX == 7 || bsize(lights) == 0 || lights.data != nullptr, "null light buffer");
+    CRT_JOIN_TAIL(ctx);
     unsigned long long* counters = nullptr;
     const int rc = inline_ray_counters(ctx, &counters);
     if (rc != CRT_OK) return rc;
@@ -377,6 +389,7 @@ extern "C" int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int
     CRT_CHECK_BUF(pixels, (size_t)W * H * 4, "pixel");
     CRT_REQUIRE(triangles.data != nullptr, "null triangle buffer");
     CRT_REQUIRE(n_rays > 0, "n_rays must be positive");
+    CRT_JOIN_TAIL(ctx);
     unsigned long long* counters = nullptr;
     const int rc = inline_ray_counters(ctx, &counters);
     if (rc != CRT_OK) return rc;

@@ -404,6 +404,7 @@ extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geo
     CRT_REQUIRE(ctx && geom, "null context or geometry");
     int rc = check_buffers(W, H, b);
     if (rc != CRT_OK) return rc;
+    CRT_JOIN_TAIL(ctx);  // the previous frame's tail owns the accumulation / pixel buffers and the second ray queue until here
     crt_buffer fin;
     crt_restir_output_buffer(options, b, &fin);
     if (!fused(options))
@@ -419,8 +420,9 @@ extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geo
     GBuf g;
     rc = ensure_gbuf(ctx, n, &g);
     if (rc != CRT_OK) return rc;
+    const bool overlap = ctx->overlap != 0 && !ctx->profiling;
     ShadowQueue q{nullptr, nullptr, nullptr, 0};
-    rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q);
+    rc = queue_prepare(ctx, (size_t)(rows.y1 - rows.y0) * W, &q, overlap ? 1 : 0);
     if (rc != CRT_OK) return rc;
     crt_float4* accum = (crt_float4*)b->accumulation.data;
     CRT_MODE_NS(ctx, launch_resolve)(
@@ -429,9 +431,25 @@ extern "C" int crt_restir_frame_end(crt_ctx* ctx, int W, int H, crt_geometry geo
         ctx->resolve_reuse && options.use_visibility_reuse);
     rc = check_launch(ctx, "resolve_fast");
     if (rc != CRT_OK) return rc;
-    rc = queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr});
+    if (!overlap)
+    {
+        rc = queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr});
+        if (rc != CRT_OK) return rc;
+        return crt_tone_mapping(ctx, b->pixels, b->accumulation, W, H);
+    }
+    // The tail — resolve rays, then tone mapping — goes to the second stream: it reads only its own ray queue (shading
+    // factors included) and reads / writes accumulation and pixels, none of which the next frame touches before its own
+    // crt_restir_frame_end, and that call (like every other entry point that touches those buffers) orders itself after
+    // this tail first (join_tail at the top of this function).
+    CRT_CUDA(cudaEventRecord(ctx->ev_head, ctx->stream));
+    CRT_CUDA(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_head, 0));
+    rc = queue_trace<kEpiResolve>(ctx, geom, q, ShadowSink{nullptr, accum, options.accumulate, nullptr}, ctx->tail_stream);
     if (rc != CRT_OK) return rc;
-    return crt_tone_mapping(ctx, b->pixels, b->accumulation, W, H);
+    rc = tone_mapping_on(ctx, ctx->tail_stream, b->pixels, b->accumulation, W, H);
+    if (rc != CRT_OK) return rc;
+    CRT_CUDA(cudaEventRecord(ctx->ev_tail, ctx->tail_stream));
+    ctx->tail_pending = true;
+    return CRT_OK;
 }
 
 extern "C" int crt_restir_di_frame(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,

@@ -68,31 +68,36 @@ inline unsigned sweep_blocks(crt_ctx* ctx, size_t n)
 }
 
 // ---- wavefront plumbing
-static int queue_prepare(crt_ctx* ctx, size_t n_pixels, ShadowQueue* q)
+// which = 1: the second queue (resolve rays of a frame whose tail overlaps the next frame, crt_set_frame_overlap)
+static int queue_prepare(crt_ctx* ctx, size_t n_pixels, ShadowQueue* q, int which = 0)
 {
-    if (ctx->queue_capacity < n_pixels)
-    {
-        if (ctx->queue_rays) CRT_CUDA(cudaFree(ctx->queue_rays));
-        ctx->queue_rays = nullptr;
-        ctx->queue_capacity = 0;
-        CRT_CUDA(cudaMalloc(&ctx->queue_rays, n_pixels * sizeof(ShadowRay)));
-        ctx->queue_capacity = n_pixels;
-    }
     if (!ctx->queue_counters)
     {
         CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 6 * sizeof(unsigned)));  // count, next, two 64-bit totals
         CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 6 * sizeof(unsigned), ctx->stream));
     }
-    CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 2 * sizeof(unsigned), ctx->stream));
-    q->rays = (ShadowRay*)ctx->queue_rays;
-    q->count = ctx->queue_counters;
-    q->next = ctx->queue_counters + 1;
-    q->capacity = (uint32_t)ctx->queue_capacity;
+    void*& rays = which ? ctx->queue2_rays : ctx->queue_rays;
+    size_t& capacity = which ? ctx->queue2_capacity : ctx->queue_capacity;
+    if (capacity < n_pixels)
+    {
+        if (rays) CRT_CUDA(cudaFree(rays));
+        rays = nullptr;
+        capacity = 0;
+        CRT_CUDA(cudaMalloc(&rays, n_pixels * sizeof(ShadowRay)));
+        capacity = n_pixels;
+    }
+    if (which && !ctx->queue2_counters) CRT_CUDA(cudaMalloc((void**)&ctx->queue2_counters, 2 * sizeof(unsigned)));
+    unsigned* counters = which ? ctx->queue2_counters : ctx->queue_counters;
+    CRT_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), ctx->stream));
+    q->rays = (ShadowRay*)rays;
+    q->count = counters;
+    q->next = counters + 1;
+    q->capacity = (uint32_t)capacity;
     q->total = (unsigned long long*)(ctx->queue_counters + 2);
     return CRT_OK;
 }
 template <int EPI>
-static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, const ShadowSink& sink)
+static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, const ShadowSink& sink, cudaStream_t on = nullptr)
 {
     static int blocks_per_sm = 0;
     if (!blocks_per_sm)
@@ -100,8 +105,9 @@ static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, co
         CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_shadow_queue<EPI>, kShadowWarps * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, ctx->stream>>>(geom->view(), q, sink);
-    return check_launch(ctx, (EPI == kEpiReservoirVisibility || EPI == kEpiSoaVisibility) ? "trace_visibility_reuse" : "trace_resolve");
+    cudaStream_t st = on ? on : ctx->stream;
+    k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, st>>>(geom->view(), q, sink);
+    return check_launch(ctx, (EPI == kEpiReservoirVisibility || EPI == kEpiSoaVisibility) ? "trace_visibility_reuse" : "trace_resolve", st);
 }
 // light records for (geometry, light list); rebuilt when another list is passed
 static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60, const uint32_t* lights, size_t n,
@@ -129,6 +135,7 @@ static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60,
 namespace crt
 {
 // force the (lazily loaded) kernels of a translation unit into the context; see crt_slab_set_links
+int tone_mapping_on(crt_ctx* ctx, cudaStream_t st, crt_buffer pixels, crt_buffer accumulation, int W, int H);
 int preload_fused_kernels();
 int preload_dropin_kernels();
 }  // namespace crt

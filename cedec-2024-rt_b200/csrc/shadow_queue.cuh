@@ -120,14 +120,15 @@ __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const Sh
 
 // One node step of the any-hit walk (the node half of walk_step): pops / descends and leaves the hit
 // triangles of the visited node in w.tmask.  Returns false when the walk has nothing left (a miss).
-__device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, const RaySetup& r)
+__device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, WalkStack& st, const RaySetup& r)
 {
     if ((w.ng_mask >> 24) == 0)
     {
         if (w.sp == 0) return false;
         --w.sp;
-        w.ng_base = w.stack_base[w.sp];
-        w.ng_mask = w.stack_mask[w.sp];
+        const WalkEntry top = st.e[w.sp];
+        w.ng_base = top.base;
+        w.ng_mask = top.mask;
     }
     const int bit = 31 - __clz((int)w.ng_mask);
     w.ng_mask &= ~(1u << bit);
@@ -135,8 +136,7 @@ __device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, const 
     const uint32_t node_idx = w.ng_base + (uint32_t)__popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
     if (w.ng_mask >> 24)
     {
-        w.stack_base[w.sp] = w.ng_base;
-        w.stack_mask[w.sp] = w.ng_mask;
+        st.e[w.sp] = WalkEntry{w.ng_base, w.ng_mask};
         ++w.sp;
     }
     uint32_t imask;
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
     r.ro = r.rd = f3{0.0f, 0.0f, 0.0f};
     uint32_t pix = 0, ray_idx = 0;
     Walk w;
+    WalkStack stack;
     w.sp = 0;
     w.ng_base = w.ng_mask = w.tri_base = w.tmask = 0;
 
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
         {
             // node phase
             bool missed = false;
-            if (active) missed = !shadow_node_step(bvh, w, r);
+            if (active) missed = !shadow_node_step(bvh, w, stack, r);
             // triangle phase: inclusive scan of the per-lane pair counts
             const uint32_t own_mask = active ? w.tmask : 0u;
             const uint32_t cnt = (uint32_t)__popc(own_mask);

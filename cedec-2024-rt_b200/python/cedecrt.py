@@ -121,6 +121,8 @@ def _load():
         "crt_shutdown": [P],
         "crt_set_math_mode": [P, I],
         "crt_set_stream": [P, C.c_void_p],
+        "crt_set_frame_overlap": [P, I],
+        "crt_frame_join": [P],
         "crt_set_row_range": [P, I, I],
         "crt_malloc": [P, C.c_size_t, C.POINTER(C.c_void_p)],
         "crt_free": [P, C.c_void_p],
@@ -181,6 +183,8 @@ def _load():
     lib.crt_device_name.argtypes = [P]
     lib.crt_get_stream.restype = C.c_void_p
     lib.crt_get_stream.argtypes = [P]
+    lib.crt_get_tail_stream.restype = C.c_void_p
+    lib.crt_get_tail_stream.argtypes = [P]
     lib.crt_shadow_rays_traced.restype = C.c_int
     lib.crt_shadow_rays_traced.argtypes = [P, C.POINTER(C.c_ulonglong)]
     lib.crt_inline_rays_traced.restype = C.c_int
@@ -323,6 +327,16 @@ class Runtime:
 
     def stream(self):
         return self.lib.crt_get_stream(self.ctx)
+
+    def set_frame_overlap(self, on=True):
+        """the fused frame's tail (resolve rays + tone mapping) on a second stream beside the next frame's head"""
+        self._check(self.lib.crt_set_frame_overlap(self.ctx, 1 if on else 0))
+
+    def frame_join(self):
+        self._check(self.lib.crt_frame_join(self.ctx))
+
+    def tail_stream(self):
+        return self.lib.crt_get_tail_stream(self.ctx)
 
     def launch_count(self):
         return int(self.lib.crt_launch_count(self.ctx))

@@ -141,13 +141,14 @@ class SlabRenderer:
     tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
 
     def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True, edges=None, options=None, p2p=True,
-                 stream=None, share=None, connect=True):
+                 stream=None, share=None, connect=True, overlap=False):
         """p2p: in fused mode with more than one rank, exchange halo rows by direct peer stores (csrc/slab_p2p.cu,
         buffers shared through cudaIpc handles) instead of NCCL send/recv; needs slabs >= HALO rows, W % 16 == 0.
         stream: the torch stream this slab's kernels go to (default: the current one).  share: another SlabRenderer on
         the same GPU whose scene, light list and BVH this one uses instead of uploading and building its own.
         connect=False leaves the neighbour links to the caller (SlabGroup: slabs of one process are linked by plain
-        pointers, `rank`/`world` then count slabs, not processes)."""
+        pointers, `rank`/`world` then count slabs, not processes).  overlap: fused mode only — the frame's tail (resolve
+        rays + tone mapping) runs on the context's second stream beside the next frame's head (crt_set_frame_overlap)."""
         import numpy as np
 
         import cedecrt
@@ -165,6 +166,11 @@ class SlabRenderer:
         self.stream = stream if stream is not None else torch.cuda.current_stream()
         assert self.stream.cuda_stream != 0, "bench needs a non-default torch stream"
         self.rt.set_stream(self.stream.cuda_stream)
+        self.overlap = bool(overlap and self.fused)
+        self._tail = None
+        if self.overlap:
+            self.rt.set_frame_overlap(True)
+            self._tail = torch.cuda.ExternalStream(self.rt.tail_stream())
         self.edges = edges if edges is not None else [slab_rows(H, world, r)[0] for r in range(world)] + [H]
         self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
         self.plan = halo_plan(H, self.edges, rank, self.halo) if world > 1 else []
@@ -292,6 +298,7 @@ class SlabRenderer:
         self.host_pixels = self.torch.empty(4 * self.W * max(self.y1 - self.y0, 1), dtype=self.torch.uint8).pin_memory()
 
     def reset_history(self):
+        self.rt.frame_join()
         with self.torch.cuda.stream(self.stream):
             for t in (self.t_tmp, self.t_r0, self.t_r1, self.t_acc):
                 t.zero_()
@@ -301,7 +308,8 @@ class SlabRenderer:
     slabs = property(lambda self: [self])
 
     def join(self):
-        pass
+        """order the slab's stream after everything of its frames (the overlapped tail included)"""
+        self.rt.frame_join()
 
     def check(self):
         stage = self.rt.slab_status() if self.p2p else 0
@@ -407,6 +415,7 @@ class SlabRenderer:
     def download_pixels(self):
         """the reference's read-back (10_restir_di.cpp:386-389): copy on the frame's own stream; the caller synchronises"""
         src = self._rows(self.t_pix, 4, self.y0, self.y1)
+        self.rt.frame_join()
         with self.torch.cuda.stream(self.stream):
             self.host_pixels.copy_(src, non_blocking=True)
 
@@ -423,7 +432,7 @@ class SlabRenderer:
         slot = self._copies % 2
         self._copies += 1
         rendered = torch.cuda.Event()
-        rendered.record(self.stream)
+        rendered.record(self._tail if self.overlap else self.stream)  # the stream tone mapping ran on
         self._copy_stream.wait_event(rendered)
         src = self._rows(self.t_pix, 4, self.y0, self.y1)
         with torch.cuda.stream(self._copy_stream):
@@ -458,7 +467,7 @@ class SlabGroup:
 
     The interface is the part of SlabRenderer's that bench.py and the tests use."""
 
-    def __init__(self, torch, dist, rank, world, tris, cam, W, H, sub=2, options=None):
+    def __init__(self, torch, dist, rank, world, tris, cam, W, H, sub=2, options=None, overlap=False):
         self.torch, self.dist, self.rank, self.world, self.W, self.H, self.sub = torch, dist, rank, world, W, H, sub
         vworld = world * sub
         edges = [slab_rows(H, vworld, r)[0] for r in range(vworld)] + [H]
@@ -469,7 +478,7 @@ class SlabGroup:
             with torch.cuda.stream(st):
                 self.slabs.append(SlabRenderer(torch, dist, rank * sub + j, vworld, tris, cam, W, H, fused=True,
                                                edges=edges, options=options, p2p=True, stream=st,
-                                               share=self.slabs[0] if j else None, connect=False))
+                                               share=self.slabs[0] if j else None, connect=False, overlap=overlap))
         assert all(s.p2p for s in self.slabs), "slabs too thin for direct halo stores (needs >= %d rows each)" % HALO
         # One whole frame of the first slab alone, in both arithmetic modes, before any slab can wait for another: it
         # builds the shared geometry's light records and has every kernel of the frame loaded (with lazy module loading
@@ -522,6 +531,8 @@ class SlabGroup:
 
     def join(self):
         """the group's first stream (the one callers time and synchronise) waits for the other slabs' streams"""
+        for s in self.slabs:
+            s.join()
         for st in self.streams[1:]:
             ev = self.torch.cuda.Event()
             ev.record(st)

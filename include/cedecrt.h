@@ -103,6 +103,17 @@ int crt_set_math_mode(crt_ctx* ctx, int mode);
  * to the image height).  Pixel coordinates, RNG keys and buffer indices stay global, so N slabs give exactly
  * the single-GPU frame; buffers are full-size and the host exchanges the halo rows the spatial pass reads. */
 int crt_set_row_range(crt_ctx* ctx, int y_begin, int y_end);
+/* Frame overlap (off by default; the reference's loop is strictly serial).  With it on, crt_restir_frame_end issues the
+ * tail of the fused frame — the resolve rays and tone mapping, which touch only their own ray queue, `accumulation` and
+ * `pixels` — to a second stream of the context, so the next frame's crt_restir_frame_begin / spatial passes run beside
+ * it and fill the drain of the persistent ray kernel (and the other way round): same images, frames still complete in
+ * order.  Every entry point that reads or writes `accumulation` / `pixels`, copies memory, synchronises or times
+ * (crt_restir_frame_end itself, crt_tone_mapping, crt_clear, crt_resolve, crt_memcpy_*, crt_sync, crt_timer_*, ...)
+ * first orders the context's stream after the tail in flight; a host that reads those buffers with its own stream
+ * operations calls crt_frame_join first, or orders its copy after crt_get_tail_stream()'s work to keep the overlap. */
+int crt_set_frame_overlap(crt_ctx* ctx, int on);
+int crt_frame_join(crt_ctx* ctx);
+void* crt_get_tail_stream(crt_ctx* ctx); /* NULL until overlap has been switched on once */
 /* use an existing CUDA stream (e.g. torch's) instead of the context's own; NULL restores it */
 int crt_set_stream(crt_ctx* ctx, void* cuda_stream);
 void* crt_get_stream(crt_ctx* ctx);

@@ -18,6 +18,7 @@ struct RayRec
     int pix;
     int occl_tri;  // index into the BVH triangle records of the occluder found (-1: unoccluded)
     unsigned nodes, tris;
+    int flag = 0;  // resolve rays: the final sample's stored visibility bit
 };
 
 static std::vector<char> read_file(const char* path)
@@ -167,6 +168,7 @@ int main(int argc, char** argv)
                    if (!d.want) return;
                    RayRec& r = rs[p.idx];
                    r.o = d.org; r.d = d.dir; r.pix = p.idx;
+                   r.flag = (int)(fin.load(p.idx).s.vis & 1u);
                    r.occl_tri = any_hit_record(bvh, d.org, d.dir, r.nodes, r.tris);
                    const float V = r.occl_tri >= 0 ? 0.0f : 1.0f;
                    write_accum(accum.data(), p.idx, sh.bg * V * sh.rad * sh.ucw, true);
@@ -271,6 +273,7 @@ int main(int argc, char** argv)
             rays_n++;
             const RaySetup rsu = setup_ray(r.o, r.d);
             Walk w;
+            WalkStack wst;
             walk_begin(w, rsu);
             for (;;)
             {
@@ -278,14 +281,14 @@ int main(int argc, char** argv)
                 {
                     if (w.sp == 0) break;
                     --w.sp;
-                    w.ng_base = w.stack_base[w.sp];
-                    w.ng_mask = w.stack_mask[w.sp];
+                    w.ng_base = wst.e[w.sp].base;
+                    w.ng_mask = wst.e[w.sp].mask;
                 }
                 const int bit = 31 - clz32(w.ng_mask);
                 w.ng_mask &= ~(1u << bit);
                 const uint32_t slot = (uint32_t)(bit - 24) ^ rsu.octinv;
                 const uint32_t node_idx = w.ng_base + (uint32_t)popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
-                if (w.ng_mask >> 24) { w.stack_base[w.sp] = w.ng_base; w.stack_mask[w.sp] = w.ng_mask; ++w.sp; }
+                if (w.ng_mask >> 24) { wst.e[w.sp] = WalkEntry{w.ng_base, w.ng_mask}; ++w.sp; }
                 uint32_t imask;
                 const uint32_t hits = intersect_node(bvh, node_idx, rsu, 0.0f, 0.99f, w.ng_base, w.tri_base, imask);
                 w.ng_mask = (hits & 0xff000000u) | imask;
@@ -356,6 +359,7 @@ int main(int argc, char** argv)
             RaySetup rsu = setup_ray(r.o, r.d);
             if (reversed) rsu.octinv ^= 7u;
             Walk w;
+            WalkStack wst;
             walk_begin(w, rsu);
             nodes = tris = 0;
             for (;;)
@@ -364,14 +368,14 @@ int main(int argc, char** argv)
                 {
                     if (w.sp == 0) return false;
                     --w.sp;
-                    w.ng_base = w.stack_base[w.sp];
-                    w.ng_mask = w.stack_mask[w.sp];
+                    w.ng_base = wst.e[w.sp].base;
+                    w.ng_mask = wst.e[w.sp].mask;
                 }
                 const int bit = 31 - clz32(w.ng_mask);
                 w.ng_mask &= ~(1u << bit);
                 const uint32_t slot = (uint32_t)(bit - 24) ^ rsu.octinv;
                 const uint32_t node_idx = w.ng_base + (uint32_t)popc(w.ng_mask & 0xffu & ((1u << slot) - 1u));
-                if (w.ng_mask >> 24) { w.stack_base[w.sp] = w.ng_base; w.stack_mask[w.sp] = w.ng_mask; ++w.sp; }
+                if (w.ng_mask >> 24) { wst.e[w.sp] = WalkEntry{w.ng_base, w.ng_mask}; ++w.sp; }
                 uint32_t imask;
                 const uint32_t hits = intersect_node(bvh, node_idx, rsu, 0.0f, 0.99f, w.ng_base, w.tri_base, imask);
                 nodes++;
@@ -401,6 +405,20 @@ int main(int argc, char** argv)
             }
             printf("any-hit order, %s rays: front-to-back nodes %.2f tris %.2f | back-to-front nodes %.2f tris %.2f\n", cls ? "resolve" : "visibility-reuse",
                    n0 / cnt, t0 / cnt, n1 / cnt, t1 / cnt);
+            if (cls)
+                for (int fl = 0; fl < 2; fl++)
+                {
+                    double a0 = 0, b0 = 0, a1 = 0, b1 = 0; size_t c2 = 0, occ = 0;
+                    for (const RayRec& r : rays)
+                    {
+                        if (r.flag != fl) continue;
+                        unsigned a, b, c, d;
+                        walk_any(r, false, a, b); walk_any(r, true, c, d);
+                        a0 += a; b0 += b; a1 += c; b1 += d; c2++; occ += r.occl_tri >= 0;
+                    }
+                    printf("   resolve rays whose sample is stored %s: %zu rays, %.1f%% occluded | front-to-back nodes %.2f tris %.2f | back-to-front nodes %.2f tris %.2f\n",
+                           fl ? "visible" : "occluded", c2, 100.0 * occ / (c2 ? c2 : 1), a0 / c2, b0 / c2, a1 / c2, b1 / c2);
+                }
         }
     }
     // dump rays for tree experiments

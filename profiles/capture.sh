@@ -7,8 +7,8 @@ N=${3:-9}
 MODE=${4:-fused}
 # every launch of frames 2-3 with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s $N -c $((2*N)) --csv \
-    --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --mode $MODE > gpurun_out/ncu_launches_${TAG}.log 2>&1
+    --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-ref-gpu --no-frame-hash --no-fast-line --mode $MODE > gpurun_out/ncu_launches_${TAG}.log 2>&1
 # one full capture of frame 2's kernels
 ncu --set full --clock-control none --import-source on -k "$K" -s $N -c $N -f -o gpurun_out/prof_${TAG} \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --mode $MODE > gpurun_out/ncu_full_${TAG}.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-ref-gpu --no-frame-hash --no-fast-line --mode $MODE > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out/ | tail -5

@@ -317,6 +317,31 @@ def test_reference_gpu_build_pins_the_argument_order(port, tmp_path):
     assert match[0] > 0.98 and match[1] < 0.5
 
 
+# ------------------------------------------------------------------ frame overlap
+def test_frame_overlap_changes_no_bit():
+    """crt_set_frame_overlap: the tail of every frame (resolve rays + tone mapping) on a second stream, beside the next
+    frame's raycast / candidate kernels — accumulation, RGBA8 and final reservoirs stay what the serial frames give"""
+    tris = staged("blocks_restir")
+    w, h, frames = 960, 540, 5
+    kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
+    serial, lapped = cedecrt.Runtime(0), cedecrt.Runtime(0)
+    lapped.set_frame_overlap(True)
+    a = cedecrt.RestirDI(serial, w, h, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
+    b = cedecrt.RestirDI(lapped, w, h, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
+    for f in range(frames):
+        a.frame()
+        b.frame()
+        if f == 2:  # a read in the middle of the sequence must see the finished frame too
+            assert same(a.pixels.to_host(), b.pixels.to_host())
+    assert same(a.accumulation.to_host(), b.accumulation.to_host())
+    assert same(a.pixels.to_host(), b.pixels.to_host())
+    assert reservoir_mismatch(a.output_reservoirs(), b.output_reservoirs()) == 0
+    assert serial.shadow_rays_traced() == lapped.shadow_rays_traced()
+    assert float(a.accumulation.to_host().view(np.float32).reshape(-1, 4)[:, :3].sum()) > 0
+    serial.close()
+    lapped.close()
+
+
 # ------------------------------------------------------------------ bench.py's frame fingerprint
 def test_bench_frame_hash(rt):
     """the frame_hash of bench.py's JSON line (config 5 at 4K, exact arithmetic, frames 1-2): deterministic, equal for
