@@ -347,11 +347,11 @@ def run_cuda(args):
     tris, cam, workload = load_workload()
     W, H = args.width, args.height
     fused = args.mode == "fused"
-    # slabs per GPU (--sub; slabs.py: SlabGroup): two slabs on two streams fill each other's ramp-up and drain gaps.
-    # Measured on two GPUs with 272 rows each — one GPU's share of a 4K frame at N = 8 — 1342 against 1251 Mpix/s
-    # (+7 %), and nothing at N = 2 at 4K where the slabs are long enough (profiles/r1/tuning_q.txt).  So by default
-    # two slabs per GPU when a GPU's share is below 300 rows, one otherwise.
-    sub = args.sub if args.sub > 0 else (2 if world > 1 and H // world < 300 else 1)
+    # slabs per GPU (--sub; slabs.py: SlabGroup): two slabs on two streams fill each other's ramp-up and drain gaps.  Round 1
+    # used two per GPU below 300 rows (+7 % on two GPUs at 272 rows each).  Frame overlap (--overlap, crt_set_frame_overlap)
+    # fills the same gaps without coupling two slabs at every spatial pass: on two GPUs at 272 rows each 1329 (neither) /
+    # 1413 (two slabs) / 1459 (both) / 1509 Mpix/s (overlap alone) — profiles/r2/tuning.txt.  So one slab per GPU by default.
+    sub = args.sub if args.sub > 0 else 1
     if not (fused and args.halo == "p2p" and W % 16 == 0 and H // (world * sub) >= HALO_ROWS + 9):
         sub = 1
     r = None

@@ -40,6 +40,25 @@ CRT_HD void shoot(const RayGen& rg, float u, float v, f3& ro, f3& rd)
     rd = normalize(to - rg.origin);
 }
 
+// ---- temporal reprojection (extension; specified by oracle/port/oracle_port.cpp: reproject_pixel,
+// restated here operation for operation).  The inverse of shoot(): to = o + forward + right (2u - 1) + up (1 - 2v); the
+// pixel whose sample point (xi / W, yi / H) is nearest to the projection of `p` in the previous frame's camera.
+CRT_HD bool reproject_pixel(const RayGen& prev, int W, int H, f3 p, int& xp, int& yp)
+{
+    const f3 forward = normalize(cross(prev.up, prev.right));
+    const f3 d = p - prev.origin;
+    const float s = dot(d, forward);
+    if (!(s > 0.0f)) return false;
+    const f3 q = d / s;
+    const float a = dot(q, prev.right) / dot(prev.right, prev.right);
+    const float b = dot(q, prev.up) / dot(prev.up, prev.up);
+    const float u = (a + 1.0f) * 0.5f;
+    const float v = (1.0f - b) * 0.5f;
+    xp = f2i_trunc(floorf(u * (float)W + 0.5f));
+    yp = f2i_trunc(floorf(v * (float)H + 0.5f));
+    return xp >= 0 && xp < W && yp >= 0 && yp < H;
+}
+
 // ---- raytrace.hpp:45-52 — origin p0 + 1e-3 n0 (core.hpp:32-36), direction p1 - p0 (not renormalised),
 // t in [0, 0.99]; the reference asks for the closest hit but only uses hit / no hit -> any-hit walk.
 CRT_HD float check_visibility(const Bvh& bvh, f3 p0, f3 n0, f3 p1)

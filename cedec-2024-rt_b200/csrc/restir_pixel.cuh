@@ -137,9 +137,12 @@ CRT_HD DeferredRay px_generate_candidate(const Pix& px, int frame, const Bvh& bv
 }
 
 // ---- 10_restir_di.cu:137-237
+// prev_cam != nullptr (extension: crt_temporal_resampling_reprojected): the previous reservoir is read at the pixel this
+// surface point had in the previous frame's camera; no history there = Reservoir{} (restir_core.cuh: reproject_pixel)
 template <class M, class RSP, class RS>
 CRT_HD void px_temporal(const Pix& px, int frame, const Bvh& bvh, const float* tris60, const crt_visibility* vis,
-                        f3 eye, const Opt& opt, const RSP& prev, const RS& cur)
+                        f3 eye, const Opt& opt, const RSP& prev, const RS& cur, const crt_raygen* prev_cam = nullptr,
+                        int W = 0, int H = 0)
 {
     const Vis v = load_vis(vis, px.idx);
     if (v.index == -1) return;
@@ -149,7 +152,14 @@ CRT_HD void px_temporal(const Pix& px, int frame, const Bvh& bvh, const float* t
     Pcg rng(hash_pcg4(px.xi, px.yi, frame, 1), 0);
     const Surf surf = surface_from_visibility(tri, v.u, v.v, eye);
     Res r = cur.load(px.idx);
-    temporal_merge<M>(bvh, surf, eye, opt, prev.load(px.idx), r, rng);
+    Res history;
+    if (prev_cam)
+    {
+        int xp, yp;
+        history = reproject_pixel(to_raygen(*prev_cam), W, H, surf.p, xp, yp) ? prev.load(xp + (H - yp - 1) * W) : empty_res();
+    }
+    else history = prev.load(px.idx);
+    temporal_merge<M>(bvh, surf, eye, opt, history, r, rng);
     cur.store(px.idx, r);
 }
 

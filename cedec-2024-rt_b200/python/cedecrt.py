@@ -146,6 +146,7 @@ def _load():
         "crt_raycast": [P, I, I, G, B, RayGenerator, B],
         "crt_generate_candidate": [P, I, I, I, G, B, B, Float3, B, Options, B],
         "crt_temporal_resampling": [P, I, I, I, G, B, B, Float3, Options, B, B],
+        "crt_temporal_resampling_reprojected": [P, I, I, I, G, B, B, Float3, Options, RayGenerator, B, B],
         "crt_save_temporal_reservoir": [P, I, I, B, B],
         "crt_spatial_resampling": [P, I, I, I, I, G, B, B, Float3, Options, B, B],
         "crt_resolve": [P, B, I, I, G, B, B, Float3, Options, B],
@@ -426,6 +427,12 @@ class Runtime:
         self._check(self.lib.crt_temporal_resampling(self.ctx, W, H, frame, geom.handle, triangles.arg(),
                                                      visibility.arg(), Float3(*eye), options, previous.arg(),
                                                      reservoirs.arg()))
+
+    def temporal_resampling_reprojected(self, W, H, frame, geom, triangles, visibility, eye, options, prev_raygen, previous,
+                                        reservoirs):
+        self._check(self.lib.crt_temporal_resampling_reprojected(self.ctx, W, H, frame, geom.handle, triangles.arg(),
+                                                                 visibility.arg(), Float3(*eye), options, prev_raygen,
+                                                                 previous.arg(), reservoirs.arg()))
 
     def save_temporal_reservoir(self, W, H, src, dst):
         self._check(self.lib.crt_save_temporal_reservoir(self.ctx, W, H, src.arg(), dst.arg()))

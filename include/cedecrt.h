@@ -191,6 +191,18 @@ int crt_generate_candidate(crt_ctx* ctx, int width, int height, int frame, crt_g
 int crt_temporal_resampling(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
                             crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
                             crt_buffer previous_reservoirs, crt_buffer reservoirs);
+/* Extension (the reference has no counterpart: 10_restir_di.cu:174-180 reads the same pixel_idx and
+ * 10_restir_di.cpp:257-267 only clears the accumulation when the camera moves).  temporal_resampling with the previous
+ * reservoir read at the pixel the current surface point had in the previous frame's camera `previous_raygen`
+ * (RayGenerator::shoot inverted, nearest sample point; no history behind that camera or outside its image); everything
+ * else — M cap, rejection heuristics, merge, random stream — is the reference kernel's.  With an unmoved camera the
+ * result equals crt_temporal_resampling bit for bit.  Specification: oracle/port/oracle_port.cpp: reproject_pixel.
+ * Per-kernel path only: the fused frame merges in place, which a lookup at another pixel forbids; with row slabs the
+ * rows of `previous_reservoirs` a slab reads are no longer bounded by the spatial halo (the host must provide all rows
+ * the camera motion can reach).  crt_launch name: "temporal_resampling_reprojected" (previous_raygen is the 9th param). */
+int crt_temporal_resampling_reprojected(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                                        crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                                        crt_raygen previous_raygen, crt_buffer previous_reservoirs, crt_buffer reservoirs);
 /* 10_restir_di.cu:239-254 — note the reference's parameter names are swapped: the first buffer is the source */
 int crt_save_temporal_reservoir(crt_ctx* ctx, int width, int height, crt_buffer src, crt_buffer dst);
 /* 10_restir_di.cu:256-388 */

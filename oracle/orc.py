@@ -199,6 +199,14 @@ class Oracle:
         self.lib.orc_temporal_resampling(W, H, frame, g, _p(tris), len(tris), _p(vis), _p(eye), _p(opt), _p(prev), _p(res))
         return res
 
+    def temporal_resampling_reprojected(self, W, H, frame, g, tris, vis, eye, opt, prev_rg, prev, res):
+        """extension (oracle/port: reproject_pixel is its specification): the previous reservoir is
+        read at the pixel the current surface point had in the previous frame's camera `prev_rg`"""
+        eye = np.asarray(eye, np.float32)
+        self.lib.orc_temporal_resampling_reprojected(W, H, frame, g, _p(tris), len(tris), _p(vis), _p(eye), _p(opt),
+                                                     _p(prev_rg), _p(prev), _p(res))
+        return res
+
     def save_temporal_reservoir(self, W, H, src, dst):
         self.lib.orc_save_temporal_reservoir(W, H, _p(src), _p(dst))
         return dst

@@ -356,8 +356,37 @@ static void k_generate_candidate(long tid, int W, int H, int frame, const Geom& 
     out[px.idx] = r;
 }
 
+// ---- temporal reprojection — NOT in the reference: 10_restir_di.cu:174-180 reads the previous
+// reservoir at the same pixel_idx and the host only clears the accumulation when the camera moves (10_restir_di.cpp:257-267).
+// This function is therefore the *specification* of the extension; the CUDA path (csrc/restir_core.cuh: reproject_pixel)
+// restates it operation for operation.
+//   The surface point of the current pixel is projected into the previous frame's camera — the inverse of
+//   RayGenerator::shoot (camera.hpp:27-35): to = o + forward + right (2u - 1) + up (1 - 2v) — and the pixel whose sample
+//   point (u, v) = (xi / W, yi / H) is nearest is taken: xi = floor(u W + 1/2), yi = floor(v H + 1/2).  Behind the previous
+//   camera or outside its image there is no history.  Whether the surface found there is the same one is left to the
+//   reference's own rejection heuristics (reservoir.hpp:61-87), which scale M by depth and normal agreement.
+//   With an unmoved camera this returns the pixel itself (the hit point lies on the pixel's own ray up to rounding), so
+//   temporal_resampling_reprojected == temporal_resampling bit for bit (tests/test_reprojection.py).
+static bool reproject_pixel(const RayGen& prev, int W, int H, V3 p, int& xp, int& yp)
+{
+    const V3 forward = normalize(cross(prev.up, prev.right));
+    const V3 d = p - prev.origin;
+    const float s = dot(d, forward);
+    if (!(s > 0.0f)) return false;
+    const V3 q = d / s;
+    const float a = dot(q, prev.right) / dot(prev.right, prev.right);
+    const float b = dot(q, prev.up) / dot(prev.up, prev.up);
+    const float u = (a + 1.0f) * 0.5f;
+    const float v = (1.0f - b) * 0.5f;
+    xp = to_int(floorf(u * (float)W + 0.5f));
+    yp = to_int(floorf(v * (float)H + 0.5f));
+    return xp >= 0 && xp < W && yp >= 0 && yp < H;
+}
+
+// prev_cam == nullptr: the reference's kernel (same pixel_idx)
 static void k_temporal(long tid, int W, int H, int frame, const Geom& g, const Visibility* vis, V3 eye,
-                       const Options& opt, const Reservoir* prev_buf, Reservoir* cur)  // 10_restir_di.cu:137-237
+                       const Options& opt, const Reservoir* prev_buf, Reservoir* cur,
+                       const RayGen* prev_cam = nullptr)  // 10_restir_di.cu:137-237
 {
     const Px px = pixel_of(tid, W, H);
     const Visibility v = vis[px.idx];
@@ -366,6 +395,12 @@ static void k_temporal(long tid, int W, int H, int frame, const Geom& g, const V
     Pcg rng(hash_pcg4(px.xi, px.yi, frame, 1), 0);
     const Surf surf = surface_from_visibility(v, g.tris, eye);
     Reservoir prev = prev_buf[px.idx];
+    if (prev_cam)
+    {
+        int xp, yp;
+        // no history: the merge below runs with Reservoir{} (M = 0, weight 0), so the random stream does not depend on it
+        prev = reproject_pixel(*prev_cam, W, H, surf.p, xp, yp) ? prev_buf[xp + (H - yp - 1) * W] : empty_reservoir();
+    }
     Reservoir r = cur[px.idx];
     const int cap = 20 * opt.ris_sample_count;  // M-cap, 10_restir_di.cu:186-188
     prev.M = prev.M < cap ? prev.M : cap;
@@ -705,6 +740,17 @@ extern "C"
                                  const float* eye, const Options* opt, const Reservoir* prev, Reservoir* res)
     {
         launch(W, H, [&](long tid) { k_temporal(tid, W, H, frame, *(Geom*)geom, vis, f3(eye), *opt, prev, res); });
+    }
+    // temporal resampling with reprojection into the previous frame's camera (extension, see reproject_pixel)
+    void orc_temporal_resampling_reprojected(int W, int H, int frame, void* geom, const Triangle*, int, const Visibility* vis,
+                                             const float* eye, const Options* opt, const RayGen* prev_cam,
+                                             const Reservoir* prev, Reservoir* res)
+    {
+        launch(W, H, [&](long tid) { k_temporal(tid, W, H, frame, *(Geom*)geom, vis, f3(eye), *opt, prev, res, prev_cam); });
+    }
+    int orc_reproject_pixel(const RayGen* prev_cam, int W, int H, const float* p, int* xy)
+    {
+        return reproject_pixel(*prev_cam, W, H, f3(p), xy[0], xy[1]) ? 1 : 0;
     }
     void orc_save_temporal_reservoir(int W, int H, const Reservoir* src, Reservoir* dst)  // 10_restir_di.cu:239-254
     {

@@ -295,6 +295,21 @@ extern "C"
                                             AosStore{(crt_reservoir*)prev}, AosStore{res});
                });
     }
+    void orc_temporal_resampling_reprojected(int W, int H, int frame, void* gp, const crt_triangle* tris, int,
+                                             const crt_visibility* vis, const float* eye, const crt_options* opt,
+                                             const crt_raygen* prev_cam, const crt_reservoir* prev, crt_reservoir* res)
+    {
+        const Bvh bvh = ((EmuGeom*)gp)->view();
+        launch(W, H, [&](Pix p)
+               {
+                   if (g_math_mode)
+                       px_temporal<Math<1>>(p, frame, bvh, (const float*)tris, vis, v3(eye), make_opt(*opt),
+                                            AosStore{(crt_reservoir*)prev}, AosStore{res}, prev_cam, W, H);
+                   else
+                       px_temporal<Math<0>>(p, frame, bvh, (const float*)tris, vis, v3(eye), make_opt(*opt),
+                                            AosStore{(crt_reservoir*)prev}, AosStore{res}, prev_cam, W, H);
+               });
+    }
     void orc_save_temporal_reservoir(int W, int H, const crt_reservoir* src, crt_reservoir* dst)
     {
         memcpy(dst, src, (size_t)W * H * sizeof(crt_reservoir));
