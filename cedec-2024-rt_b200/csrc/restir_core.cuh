@@ -40,8 +40,8 @@ CRT_HD void shoot(const RayGen& rg, float u, float v, f3& ro, f3& rd)
     rd = normalize(to - rg.origin);
 }
 
-// ---- temporal reprojection (extension; specified by oracle/port/oracle_port.cpp: reproject_pixel,
-// restated here operation for operation).  The inverse of shoot(): to = o + forward + right (2u - 1) + up (1 - 2v); the
+// ---- temporal reprojection (extension; the specification is the checker's reproject_pixel — see
+// DESIGN.md section 11 — restated here operation for operation).  The inverse of shoot(): to = o + forward + right (2u - 1) + up (1 - 2v); the
 // pixel whose sample point (xi / W, yi / H) is nearest to the projection of `p` in the previous frame's camera.
 CRT_HD bool reproject_pixel(const RayGen& prev, int W, int H, f3 p, int& xp, int& yp)
 {

@@ -554,10 +554,16 @@ class RestirDI:
     """The application loop of examples/10_restir_di/10_restir_di.cpp:96-122,184-226,229-380, headless:
     buffers live on the device, one `frame()` issues the reference's launch list on the context's stream."""
 
-    def __init__(self, rt, width, height, triangles_host, eye, lookat_pt, options=None, fused=False):
+    def __init__(self, rt, width, height, triangles_host, eye, lookat_pt, options=None, fused=False, reproject=False):
         """fused=False: the reference's launch list, one crt_* call per kernel, AoS reservoir buffers (drop-in mode);
-        fused=True: one crt_restir_di_frame call per frame (SoA reservoirs inside the same buffers)."""
+        fused=True: one crt_restir_di_frame call per frame (SoA reservoirs inside the same buffers).
+        reproject=True (extension, launch-list mode only): temporal resampling looks the previous reservoir up at the pixel
+        the surface point had in the previous frame's camera (crt_temporal_resampling_reprojected); set_camera() moves the
+        camera and clears the accumulation like the reference's loop (10_restir_di.cpp:257-267)."""
+        if fused and reproject:
+            raise CrtError("temporal reprojection runs on the per-kernel path: the fused frame merges the history in place")
         self.rt, self.W, self.H, self.fused = rt, width, height, fused
+        self.reproject, self.prev_raygen = reproject, None
         n = width * height
         self.options = options or Options()
         self.eye = tuple(float(np.float32(v)) for v in eye)
@@ -575,6 +581,11 @@ class RestirDI:
         self.output = self.reservoir1
         self.frame_index = 0
         rt.clear(self.accumulation, width, height)
+
+    def set_camera(self, eye, lookat_pt):
+        self.eye = tuple(float(np.float32(v)) for v in eye)
+        self.raygen = lookat(eye, lookat_pt, self.W, self.H)
+        self.rt.clear(self.accumulation, self.W, self.H)
 
     def output_reservoirs(self):
         """final reservoirs of the last frame in the reference's AoS layout (host numpy array)"""
@@ -603,7 +614,11 @@ class RestirDI:
             return
         rt.raycast(W, H, g, t, self.raygen, v)
         rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
-        rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        if self.reproject and self.prev_raygen is not None:
+            rt.temporal_resampling_reprojected(W, H, f, g, t, v, eye, o, self.prev_raygen, self.temporal, self.reservoir0)
+        else:
+            rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        self.prev_raygen = RayGenerator.from_buffer_copy(bytes(self.raygen))
         rt.save_temporal_reservoir(W, H, self.reservoir0, self.temporal)
         bi, bo = self.reservoir0, self.reservoir1
         for k in range(o.spatial_resampling_passes):

@@ -248,8 +248,12 @@ class Oracle:
 class RestirChain:
     """The frame loop of 10_restir_di.cpp:229-380 driven over any object with the Oracle kernel methods."""
 
-    def __init__(self, orc, W, H, tris, g, eye, center, opt, lights=None):
+    def __init__(self, orc, W, H, tris, g, eye, center, opt, lights=None, reproject=False):
+        """reproject=True (extension): temporal resampling reads the previous reservoir at the pixel
+        the surface point had in the previous frame's camera; set_camera() moves the camera between frames and clears the
+        accumulation like the reference does on a move (10_restir_di.cpp:257-267)"""
         self.o, self.W, self.H, self.tris, self.g, self.opt = orc, W, H, tris, g, opt
+        self.reproject, self.prev_rg = reproject, None
         self.eye = np.asarray(eye, np.float32)
         self.rg = orc.lookat(eye, center, W, H)
         self.lights = light_indices(tris) if lights is None else lights
@@ -262,12 +266,21 @@ class RestirChain:
         self.frame = 0
         self.out = self.buf1
 
+    def set_camera(self, eye, center):
+        self.eye = np.asarray(eye, np.float32)
+        self.rg = self.o.lookat(eye, center, self.W, self.H)
+        self.accum[:] = 0  # `clear` on a camera move (10_restir_di.cpp:257-267)
+
     def step(self):
         o, W, H, g, t, opt, eye = self.o, self.W, self.H, self.g, self.tris, self.opt, self.eye
         self.frame += 1  # first frame is 1 (10_restir_di.cpp:233)
         o.raycast(W, H, g, t, self.rg, self.vis)
         o.generate_candidate(W, H, self.frame, g, t, self.vis, eye, self.lights, opt, self.buf0)
-        o.temporal_resampling(W, H, self.frame, g, t, self.vis, eye, opt, self.temporal, self.buf0)
+        if self.reproject and self.prev_rg is not None:
+            o.temporal_resampling_reprojected(W, H, self.frame, g, t, self.vis, eye, opt, self.prev_rg, self.temporal, self.buf0)
+        else:
+            o.temporal_resampling(W, H, self.frame, g, t, self.vis, eye, opt, self.temporal, self.buf0)
+        self.prev_rg = self.rg.copy()
         o.save_temporal_reservoir(W, H, self.buf0, self.temporal)
         bi, bo = self.buf0, self.buf1
         for k in range(int(opt["spatial_resampling_passes"])):

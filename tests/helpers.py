@@ -99,6 +99,13 @@ class DeviceAsOracle:
         res[:] = d_r.to_host()
         return res
 
+    def temporal_resampling_reprojected(self, W, H, frame, g, tris, vis, eye, opt, prev_rg, prev, res):
+        d_v, d_p, d_r = self.rt.to_device(vis), self.rt.to_device(prev), self.rt.to_device(res)
+        self.rt.temporal_resampling_reprojected(W, H, frame, g, g.triangles, d_v, tuple(eye), self._opt(opt), self._rg(prev_rg),
+                                                d_p, d_r)
+        res[:] = d_r.to_host()
+        return res
+
     def save_temporal_reservoir(self, W, H, src, dst):
         d_s, d_d = self.rt.to_device(src), self.rt.to_device(dst)
         self.rt.save_temporal_reservoir(W, H, d_s, d_d)

@@ -317,6 +317,50 @@ def test_reference_gpu_build_pins_the_argument_order(port, tmp_path):
     assert match[0] > 0.98 and match[1] < 0.5
 
 
+# ------------------------------------------------------------------ temporal reprojection (extension)
+def test_temporal_reprojection_bit_exact_with_a_moving_camera(rt, exact, port):
+    """crt_temporal_resampling_reprojected against its specification (oracle/port: reproject_pixel): the chain with two
+    camera moves on blocks_restir at 480x270, exact arithmetic — stage outputs and accumulation bit for bit; the resident
+    host loop (cedecrt.RestirDI(reproject=True).set_camera) gives the same frames; and by name through crt_launch"""
+    from test_reprojection import KW, moved_camera_chain
+
+    tris = small_scene("blocks_ao").copy()
+    tris["emissive"][100:140] = (5.0, 4.0, 3.0)
+    w, h = 128, 72
+    a = moved_camera_chain(port, tris, w, h, 1, True)
+    b = moved_camera_chain(exact, tris, w, h, 1, True)
+    rt.set_math_mode(cedecrt.MATH_EXACT)
+    port.set_math_mode(1)
+    assert same(a.vis["index"], b.vis["index"]) and same(a.vis["uv"], b.vis["uv"])
+    assert reservoir_mismatch(a.temporal, b.temporal) == 0 and reservoir_mismatch(a.out, b.out) == 0
+    assert same(a.accum, b.accum) and float(a.accum[:, :3].sum()) > 0
+    # the resident loop
+    app = cedecrt.RestirDI(rt, w, h, tris, *CAM_AO, cedecrt.Options(**KW), reproject=True)
+    for _ in range(2):
+        app.frame()
+    app.set_camera((8.4, 7.8, 8.1), (0.1, 0.0, -0.1))
+    app.frame()
+    prev_rg = cedecrt.RayGenerator.from_buffer_copy(bytes(app.prev_raygen))
+    app.set_camera((8.9, 7.5, 8.3), (0.2, 0.1, -0.2))
+    app.frame()
+    assert same(app.accumulation.to_host().view(np.float32).reshape(-1, 4), a.accum)
+    assert reservoir_mismatch(app.temporal.to_host(), a.temporal) == 0
+    # by name: frame 4's temporal step again, from the same inputs
+    n = w * h
+    cand = rt.buffer(cedecrt.RESERVOIR, n)
+    eye = cedecrt.Float3(*app.eye)
+    rt.generate_candidate(w, h, 4, app.geom, app.triangles, app.visibility, app.eye, app.lights, app.options, cand)
+    one, two = rt.to_device(cand.to_host()), rt.to_device(cand.to_host())
+    hist = rt.to_device(a.temporal)  # any history will do: both calls read the same
+    rt.temporal_resampling_reprojected(w, h, 4, app.geom, app.triangles, app.visibility, app.eye, app.options, prev_rg, hist, one)
+    rt.launch("temporal_resampling_reprojected", w, h, 4, app.geom, app.triangles, app.visibility, eye, app.options, prev_rg, hist, two)
+    assert same(one.to_host(), two.to_host())
+    with pytest.raises(cedecrt.CrtError, match="in place"):
+        rt.temporal_resampling_reprojected(w, h, 4, app.geom, app.triangles, app.visibility, app.eye, app.options, prev_rg, one, one)
+    with pytest.raises(cedecrt.CrtError, match="per-kernel path"):
+        cedecrt.RestirDI(rt, w, h, tris, *CAM_AO, cedecrt.Options(**KW), fused=True, reproject=True)
+
+
 # ------------------------------------------------------------------ frame overlap
 def test_frame_overlap_changes_no_bit():
     """crt_set_frame_overlap: the tail of every frame (resolve rays + tone mapping) on a second stream, beside the next
