@@ -325,6 +325,40 @@ struct alignas(8) WalkStack
 {
     WalkEntry e[kStackSize];
 };
+// MEASURED AND REJECTED (kept behind -DCRT_RAYS_PER_LANE; profiles/r2/tuning.txt): 06_ao at 32 rays 17.5 ms per frame with
+// the reference's lockstep loop over rays, 23.0 ms with this loop (26.7 ms without the start-together rule); 09_ris with
+// the shadowed target 179.7 against 203.2 ms.  The walks of these single-kernel examples are short (a 3 034-triangle
+// scene; any-hit rays that stop early), so the two ballots and the re-entered walk_step per iteration cost more than
+// the idle lanes they save.
+// Per-lane ray loops (px_ao, ris_candidates_shadowed): every lane walks its own sequence of rays, one walk step per
+// iteration, and draws its next ray when the current one is decided — instead of all lanes waiting for the warp's longest
+// walk of the same ray index.  Two things keep that efficient: the lanes that entered the loop together stay together
+// until the last one is finished (the ballots name the entry mask, so every iteration reconverges there), and a lane
+// waits for its next ray until at least kStartTogether lanes wait with it or nobody walks any more, so that ray set-up
+// (sampling, IEEE divisions, sinf / cosf) runs with many lanes.  (Starting each lane's ray the moment it was free made
+// 06_ao at 32 rays 17.4 -> 26.7 ms per frame: the set-up then ran in almost every iteration for one or two lanes.)
+constexpr int kStartTogether = 8;
+struct RayLoop
+{
+#if defined(__CUDA_ARCH__)
+    unsigned mask;
+    __device__ __forceinline__ RayLoop() : mask(__activemask()) {}
+    // false: every lane of the loop is finished.  start: lanes that want a ray may set it up in this iteration.
+    __device__ __forceinline__ bool next(bool wants_a_ray, bool walking, bool& start) const
+    {
+        const unsigned w = __ballot_sync(mask, wants_a_ray), b = __ballot_sync(mask, walking);
+        start = __popc(w) >= kStartTogether || b == 0u;
+        return (w | b) != 0u;
+    }
+#else
+    bool next(bool wants_a_ray, bool walking, bool& start) const
+    {
+        start = true;
+        return wants_a_ray || walking;
+    }
+#endif
+};
+
 struct Walk
 {
     int sp;

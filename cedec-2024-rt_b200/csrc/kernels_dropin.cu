@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256)
     count_rays(ray_counters, n & 0xffffu, n >> 16);
 }
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)  // 80 registers: the walk-step loop would otherwise take 128 and halve the resident warps
     k_ao(uint32_t* pixels, crt_raygen raygen, int W, int H, Rows rows, Bvh bvh, const float* tris60, int n_rays,
          unsigned long long* ray_counters)
 {

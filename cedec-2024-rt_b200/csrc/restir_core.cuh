@@ -315,10 +315,9 @@ CRT_HD Opt make_opt(const crt_options& o)
 // RIS over the emissive triangles: generate_candidate (10_restir_di.cu:78-111) and 09_ris.cu:66-100.
 // Randoms are drawn left to right: light pick, two barycentric randoms, then the reservoir's u.
 // One candidate: Reservoir::update (reservoir.hpp:22-29) with weight p_hat / light_pdf
-CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, float inv_n, float u, bool shadowed, Res& r)
+CRT_HD void ris_apply(const Surf& surf, const LightSample& ls, float inv_n, float u, float p_hat, Res& r)
 {
     const float light_pdf = inv_n * 1.0f / ls.area;  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
-    const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
     const float weight = p_hat / light_pdf;
     r.w_sum += weight;
     r.M += 1;
@@ -332,6 +331,10 @@ CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, 
         r.s.vis = 0;
     }
 }
+CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, float inv_n, float u, bool shadowed, Res& r)
+{
+    ris_apply(surf, ls, inv_n, u, target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed), r);
+}
 // The four randoms of a candidate do not depend on earlier candidates, so the light records of kRisBatch
 // candidates are requested before the first one is used: kRisBatch gathers in flight per thread instead of one
 // (the loop was latency-bound on that gather: profiles/r1/source_g_k_generate_candidate.txt, 59 % long-scoreboard).
@@ -340,10 +343,68 @@ CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, 
 #endif
 constexpr int kRisBatch = CRT_RIS_BATCH;
 // pair_mask: see LightsTable::fetch; every lane named in it must run this loop with the same `count`
+// 09_ris.cu:66-100 with use_shadowed_target_function: every candidate's target function holds a shadow ray
+// (reservoir.hpp:42-59).  The `count` walks run as one loop over walk steps: a lane whose ray is decided applies the
+// candidate (Reservoir::update) and draws the next one at once, instead of every lane of the warp waiting for the longest
+// walk of the same candidate index.  Per lane the candidates, their randoms and their order are unchanged; the target
+// function is evaluated in the reference's order ((1/pi * G) * V) * luminance.
+template <class L>
+CRT_HD Res ris_candidates_shadowed(const Bvh& bvh, const L& lights, const Surf& surf, int count, Pcg& rng)
+{
+    Res r = empty_res();
+    const float inv_n = 1.0f / (float)lights.n;
+    int c = 0;
+    bool walking = false;
+    LightSample ls;
+    ls.p = ls.n = ls.emissive = f3{0.0f, 0.0f, 0.0f};
+    ls.area = 0.0f;
+    float u = 0.0f, inv_pi_g = 0.0f;
+    RaySetup ray;
+    Walk w;
+    WalkStack stack;
+    Hit h;
+    const RayLoop loop;
+    for (;;)
+    {
+        bool start;
+        if (!loop.next(!walking && c < count, walking, start)) break;
+        if (start && !walking && c < count)
+        {
+            const float r0 = rng.next_f();
+            const float r1 = rng.next_f();
+            const float r2 = rng.next_f();
+            u = rng.next_f();
+            ls = lights.finish(lights.fetch(r0), r1, r2);
+            inv_pi_g = kInvPi * geometry_term(surf.p, surf.n, ls.p, ls.n);
+            ray = setup_ray(surf.p + 0.001f * surf.n, ls.p - surf.p, true);  // check_visibility's segment, far end first
+            walk_begin(w, ray);
+            h.prim = -1;
+            h.t = 0.99f;
+            h.u = h.v = 0.0f;
+            walking = true;
+        }
+        if (walking)
+        {
+            const int state = walk_step<true, true>(bvh, w, stack, ray, 0.0f, h, CRT_LANES_WALKING());
+            if (state != kWalkContinue)
+            {
+                const float V = state == kWalkHitAny ? 0.0f : 1.0f;
+                ris_apply(surf, ls, inv_n, u, inv_pi_g * V * luminance(ls.emissive), r);
+                ++c;
+                walking = false;
+            }
+        }
+    }
+    return r;
+}
+
 template <class L>
 CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int count, bool shadowed, Pcg& rng,
                           unsigned pair_mask = 0u)
 {
+#if defined(CRT_RAYS_PER_LANE)  // measured and rejected, see RayLoop (bvh.cuh)
+    if (shadowed) return ris_candidates_shadowed(bvh, lights, surf, count, rng);
+#endif
     Res r = empty_res();
     const float inv_n = 1.0f / (float)lights.n;
     int i = 0;

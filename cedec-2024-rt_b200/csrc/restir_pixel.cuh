@@ -329,6 +329,19 @@ CRT_HD uint32_t px_ao(const Pix& px, const crt_raygen& raygen, int W, int H, con
     const f3 ao_ro = ro + rd * h.t + n * 0.0001f;
     int n_visible = 0;
     ao_rays_traced = (uint32_t)(n_rays > 0 ? n_rays : 0);
+#if !defined(CRT_RAYS_PER_LANE)
+    // the reference's loop shape: all lanes trace their i-th ray together (the per-lane loop below is slower, see RayLoop)
+    for (int i = 0; i < n_rays; i++)
+    {
+        const float r0 = rng.next_f();
+        const float r1 = rng.next_f();
+        const float r2 = rng.next_f();
+        const f3 s = sample_hemisphere<M>(r0, r1, r2);
+        const f3 ao_rd = t0 * s.x + t1 * s.z + n * s.y;
+        Hit ah;
+        if (!trace<true>(bvh, ao_ro, ao_rd, 0.0f, kFltMax, ah)) n_visible++;
+    }
+#else
     // The n_rays walks of a pixel as one loop over walk steps: a lane whose ray is decided draws its next ray at once
     // instead of waiting for the warp's longest walk of the same ray index (the reference's `for` over rays traced in
     // lockstep ran at a third of the lanes: bench --config 06, profiles/r2/tuning.txt).  Per lane the rays, their random
@@ -339,9 +352,12 @@ CRT_HD uint32_t px_ao(const Pix& px, const crt_raygen& raygen, int W, int H, con
     Walk w;
     WalkStack stack;
     Hit ah;
-    while (i < n_rays)
+    const RayLoop loop;
+    for (;;)
     {
-        if (!walking)
+        bool start;
+        if (!loop.next(!walking && i < n_rays, walking, start)) break;
+        if (start && !walking && i < n_rays)
         {
             const float r0 = rng.next_f();
             const float r1 = rng.next_f();
@@ -356,14 +372,18 @@ CRT_HD uint32_t px_ao(const Pix& px, const crt_raygen& raygen, int W, int H, con
             ah.u = ah.v = 0.0f;
             walking = true;
         }
-        const int state = walk_step<true, true>(bvh, w, stack, r, 0.0f, ah, CRT_LANES_WALKING());
-        if (state != kWalkContinue)
+        if (walking)
         {
-            if (state == kWalkDone) n_visible++;
-            i++;
-            walking = false;
+            const int state = walk_step<true, true>(bvh, w, stack, r, 0.0f, ah, CRT_LANES_WALKING());
+            if (state != kWalkContinue)
+            {
+                if (state == kWalkDone) n_visible++;
+                i++;
+                walking = false;
+            }
         }
     }
+#endif
     const float ao = (float)n_visible / (float)n_rays;
     const uint32_t c = (uint32_t)(M::pow(ao, 1.0f / 2.2f) * 255.0f) & 0xffu;
     return c | (c << 8) | (c << 16) | (255u << 24);

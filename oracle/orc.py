@@ -280,7 +280,7 @@ class RestirChain:
             o.temporal_resampling_reprojected(W, H, self.frame, g, t, self.vis, eye, opt, self.prev_rg, self.temporal, self.buf0)
         else:
             o.temporal_resampling(W, H, self.frame, g, t, self.vis, eye, opt, self.temporal, self.buf0)
-        self.prev_rg = self.rg.copy()
+        self.prev_rg = self.rg  # set_camera replaces the object, it never mutates it
         o.save_temporal_reservoir(W, H, self.buf0, self.temporal)
         bi, bo = self.buf0, self.buf1
         for k in range(int(opt["spatial_resampling_passes"])):

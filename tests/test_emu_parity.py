@@ -80,11 +80,15 @@ def test_option_variants(emu, port):
         assert same(outs[0][2], outs[1][2]), kw
 
 
-@pytest.mark.parametrize("ex", [7, 8, 9])
+@pytest.mark.parametrize("ex", [7, 8, 9, 109])
 def test_path_tracers(emu, port, ex):
+    """109: example 09 with use_shadowed_target_function (BASELINE config 4): a shadow ray inside every candidate's target
+    function — the CUDA path walks those in a per-lane loop of walk steps (restir_core.cuh: ris_candidates_shadowed)"""
     tris = small_scene("cornellbox1")
     W, H = 64, 36
-    opt = orc.make_options(accumulate=1, max_depth=4, ris_sample_count=8, sky_color=(0.1, 0.2, 0.3))
+    opt = orc.make_options(accumulate=1, max_depth=4, ris_sample_count=8, sky_color=(0.1, 0.2, 0.3),
+                           use_shadowed_target_function=1 if ex == 109 else 0)
+    ex = 9 if ex == 109 else ex
     lights = orc.light_indices(tris)
     outs = []
     for o in (port, emu):
