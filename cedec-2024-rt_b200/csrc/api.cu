@@ -66,6 +66,14 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
         cudaEventDestroy(ctx->ev_head);
         cudaEventDestroy(ctx->ev_tail);
     }
+    if (ctx->head_stream)
+    {
+        cudaStreamSynchronize(ctx->head_stream);
+        cudaStreamDestroy(ctx->head_stream);
+        cudaEventDestroy(ctx->ev_ray_ready);
+        cudaEventDestroy(ctx->ev_vis_consumed);
+    }
+    if (ctx->vis_next) cudaFree(ctx->vis_next);
     if (ctx->queue2_rays) cudaFree(ctx->queue2_rays);
     if (ctx->queue2_counters) cudaFree(ctx->queue2_counters);
     cudaEventDestroy(ctx->ev_start);

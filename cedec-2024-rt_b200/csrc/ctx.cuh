@@ -30,6 +30,15 @@ struct crt_ctx
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
     bool tail_pending = false;  // a tail has been issued that ctx->stream has not been ordered after yet
+    // the next frame's primary rays ahead of time (crt_restir_prefetch_raycast): a third stream and a second Visibility buffer
+    cudaStream_t head_stream = nullptr;
+    cudaEvent_t ev_ray_ready = nullptr, ev_vis_consumed = nullptr;
+    void* vis_next = nullptr;
+    size_t vis_next_pixels = 0;
+    bool ray_next_valid = false, vis_consumed_pending = false;
+    crt_raygen ray_next_cam = {};
+    unsigned long long ray_next_geom = 0;
+    int ray_next_dims[4] = {0, 0, 0, 0};  // W, H, y0, y1
     void* queue2_rays = nullptr;  // the resolve rays' own queue while frames overlap (the next frame's visibility-reuse rays use the first)
     unsigned* queue2_counters = nullptr;
     size_t queue2_capacity = 0;

@@ -168,6 +168,68 @@ extern "C" int crt_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_bu
     return check_launch(ctx, "raycast");
 }
 
+// ---- primary rays of the next frame, ahead of time (frame overlap; include/cedecrt.h)
+extern "C" int crt_restir_prefetch_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_raygen raygen)
+{
+    CRT_REQUIRE(ctx && geom, "null context or geometry");
+    CRT_CHECK_IMAGE(W, H);
+    if (!ctx->overlap || ctx->profiling) return CRT_OK;  // strictly serial frames: the next crt_restir_frame_begin traces its own rays
+    const size_t n = (size_t)W * H;
+    if (!ctx->head_stream)
+    {
+        CRT_CUDA(cudaSetDevice(ctx->device));
+        CRT_CUDA(cudaStreamCreateWithFlags(&ctx->head_stream, cudaStreamNonBlocking));
+        CRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_ray_ready, cudaEventDisableTiming));
+        CRT_CUDA(cudaEventCreateWithFlags(&ctx->ev_vis_consumed, cudaEventDisableTiming));
+    }
+    if (ctx->vis_next_pixels < n)
+    {
+        CRT_CUDA(cudaStreamSynchronize(ctx->head_stream));
+        if (ctx->vis_next) CRT_CUDA(cudaFree(ctx->vis_next));
+        ctx->vis_next = nullptr;
+        ctx->vis_next_pixels = 0;
+        CRT_CUDA(cudaMalloc(&ctx->vis_next, n * sizeof(crt_visibility)));
+        ctx->vis_next_pixels = n;
+    }
+    if (ctx->vis_consumed_pending)  // the frame in flight may still be copying the previous prefetch out of the buffer
+    {
+        CRT_CUDA(cudaStreamWaitEvent(ctx->head_stream, ctx->ev_vis_consumed, 0));
+        ctx->vis_consumed_pending = false;
+    }
+    const Rows rows = rows_of(ctx, H);
+    k_raycast<<<tile_grid(W, rows), 256, 0, ctx->head_stream>>>(W, H, rows, geom->view(), raygen, (crt_visibility*)ctx->vis_next);
+    const int rc = check_launch(ctx, "raycast", ctx->head_stream);
+    if (rc != CRT_OK) return rc;
+    CRT_CUDA(cudaEventRecord(ctx->ev_ray_ready, ctx->head_stream));
+    ctx->ray_next_cam = raygen;
+    ctx->ray_next_geom = geom->serial;
+    ctx->ray_next_dims[0] = W; ctx->ray_next_dims[1] = H; ctx->ray_next_dims[2] = rows.y0; ctx->ray_next_dims[3] = rows.y1;
+    ctx->ray_next_valid = true;
+    return CRT_OK;
+}
+namespace crt
+{
+// crt_raycast, or — when the very same rays were traced ahead of time — a copy of their Visibility rows
+int raycast_or_prefetched(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_raygen raygen, crt_buffer visibility)
+{
+    const Rows rows = rows_of(ctx, H);
+    const bool hit = ctx->ray_next_valid && ctx->ray_next_geom == geom->serial && !memcmp(&ctx->ray_next_cam, &raygen, sizeof raygen) &&
+                     ctx->ray_next_dims[0] == W && ctx->ray_next_dims[1] == H && ctx->ray_next_dims[2] == rows.y0 &&
+                     ctx->ray_next_dims[3] == rows.y1 && !ctx->profiling;
+    ctx->ray_next_valid = false;
+    if (!hit) return crt_raycast(ctx, W, H, geom, triangles, raygen, visibility);
+    CRT_CHECK_BUF(visibility, (size_t)W * H, "visibility");
+    const size_t first = (size_t)(H - rows.y1) * W, count = (size_t)(rows.y1 - rows.y0) * W;
+    CRT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ray_ready, 0));
+    if (count)
+        CRT_CUDA(cudaMemcpyAsync((crt_visibility*)visibility.data + first, (const crt_visibility*)ctx->vis_next + first,
+                                 count * sizeof(crt_visibility), cudaMemcpyDeviceToDevice, ctx->stream));
+    CRT_CUDA(cudaEventRecord(ctx->ev_vis_consumed, ctx->stream));
+    ctx->vis_consumed_pending = true;
+    return CRT_OK;
+}
+}  // namespace crt
+
 extern "C" int crt_generate_candidate(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, crt_buffer triangles,
                                       crt_buffer visibility_buffer, crt_float3 eye, crt_buffer lights,
                                       crt_options options, crt_buffer reservoirs)

@@ -299,7 +299,7 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     CRT_REQUIRE(ctx && geom, "null context or geometry");
     int rc = check_buffers(W, H, b);
     if (rc != CRT_OK) return rc;
-    rc = crt_raycast(ctx, W, H, geom, triangles, raygen, b->visibility);
+    rc = raycast_or_prefetched(ctx, W, H, geom, triangles, raygen, b->visibility);
     if (rc != CRT_OK) return rc;
     ctx->frame_fused = fused(options);
     if (ctx->links_set)

@@ -135,6 +135,7 @@ static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60,
 namespace crt
 {
 // force the (lazily loaded) kernels of a translation unit into the context; see crt_slab_set_links
+int raycast_or_prefetched(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_raygen raygen, crt_buffer visibility);
 int tone_mapping_on(crt_ctx* ctx, cudaStream_t st, crt_buffer pixels, crt_buffer accumulation, int W, int H);
 int preload_fused_kernels();
 int preload_dropin_kernels();

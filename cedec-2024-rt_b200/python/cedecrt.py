@@ -123,6 +123,7 @@ def _load():
         "crt_set_stream": [P, C.c_void_p],
         "crt_set_frame_overlap": [P, I],
         "crt_frame_join": [P],
+        "crt_restir_prefetch_raycast": [P, I, I, G, RayGenerator],
         "crt_set_row_range": [P, I, I],
         "crt_malloc": [P, C.c_size_t, C.POINTER(C.c_void_p)],
         "crt_free": [P, C.c_void_p],
@@ -332,6 +333,10 @@ class Runtime:
     def set_frame_overlap(self, on=True):
         """the fused frame's tail (resolve rays + tone mapping) on a second stream beside the next frame's head"""
         self._check(self.lib.crt_set_frame_overlap(self.ctx, 1 if on else 0))
+
+    def restir_prefetch_raycast(self, W, H, geom, raygen):
+        """overlap mode: the next frame's primary rays now, on a third stream (no-op otherwise)"""
+        self._check(self.lib.crt_restir_prefetch_raycast(self.ctx, W, H, geom.handle, raygen))
 
     def frame_join(self):
         self._check(self.lib.crt_frame_join(self.ctx))
@@ -564,6 +569,7 @@ class RestirDI:
             raise CrtError("temporal reprojection runs on the per-kernel path: the fused frame merges the history in place")
         self.rt, self.W, self.H, self.fused = rt, width, height, fused
         self.reproject, self.prev_raygen = reproject, None
+        self.prefetch = False  # fused + crt_set_frame_overlap: trace the next frame's primary rays right after issuing a frame
         n = width * height
         self.options = options or Options()
         self.eye = tuple(float(np.float32(v)) for v in eye)
@@ -611,6 +617,8 @@ class RestirDI:
         if self.fused:
             bufs = rt.restir_buffers(self.pixels, self.accumulation, v, self.reservoir0, self.reservoir1, self.temporal)
             rt.restir_di_frame(W, H, f, g, t, self.raygen, eye, self.lights, o, bufs)
+            if self.prefetch:
+                rt.restir_prefetch_raycast(W, H, g, self.raygen)
             return
         rt.raycast(W, H, g, t, self.raygen, v)
         rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)

@@ -370,6 +370,8 @@ class SlabRenderer:
         f = self.frame_index
         if self.fused:
             rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
+            if self.overlap:
+                rt.restir_prefetch_raycast(W, H, g, self.raygen)  # the next frame's camera (static here)
             for k in range(o.spatial_resampling_passes):  # temporal -> r1 -> r0 -> r1 (include/cedecrt.h)
                 self.exchange(self.t_tmp if k == 0 else (self.t_r1 if k % 2 else self.t_r0), SOA_RESERVOIR)
                 rt.restir_spatial_pass(W, H, f, k, g, t, eye, o, self.bufs)
@@ -404,6 +406,8 @@ class SlabRenderer:
         if stage == 0:
             self.frame_index += 1
             rt.restir_frame_begin(W, H, self.frame_index, g, t, self.raygen, eye, self.lights, o, self.bufs)
+            if self.overlap:
+                rt.restir_prefetch_raycast(W, H, g, self.raygen)  # the next frame's camera (static here)
         elif stage <= passes:
             k = stage - 1  # input of pass k: temporal, reservoir1, reservoir0, ...
             rt.slab_exchange(W, H, 0 if k == 0 else (2 if k % 2 else 1), self.bufs)  # rows were mirrored by the kernels

@@ -112,6 +112,12 @@ int crt_set_row_range(crt_ctx* ctx, int y_begin, int y_end);
  * first orders the context's stream after the tail in flight; a host that reads those buffers with its own stream
  * operations calls crt_frame_join first, or orders its copy after crt_get_tail_stream()'s work to keep the overlap. */
 int crt_set_frame_overlap(crt_ctx* ctx, int on);
+/* With overlap on: trace the primary rays of the NEXT frame now, on a third stream and into a Visibility buffer of the
+ * context's own, beside the kernels of the frame in flight (raycast, 10_restir_di.cu:9-34, needs nothing but the camera
+ * and the geometry).  The next crt_restir_frame_begin / crt_restir_di_frame that arrives with exactly this camera,
+ * geometry, image size and row range copies those rows into its `visibility` buffer instead of tracing them; any other
+ * call traces as usual and the prefetch is dropped.  A no-op while overlap is off. */
+int crt_restir_prefetch_raycast(crt_ctx* ctx, int width, int height, crt_geometry geom, crt_raygen next_raygen);
 int crt_frame_join(crt_ctx* ctx);
 void* crt_get_tail_stream(crt_ctx* ctx); /* NULL until overlap has been switched on once */
 /* use an existing CUDA stream (e.g. torch's) instead of the context's own; NULL restores it */

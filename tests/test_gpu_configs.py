@@ -372,6 +372,8 @@ def test_frame_overlap_changes_no_bit():
     lapped.set_frame_overlap(True)
     a = cedecrt.RestirDI(serial, w, h, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
     b = cedecrt.RestirDI(lapped, w, h, tris, *CAM_RESTIR, cedecrt.Options(**kw), fused=True)
+    b.prefetch = True  # and the next frame's primary rays traced ahead of time on a third stream
+    launches = lapped.launch_count(), serial.launch_count()
     for f in range(frames):
         a.frame()
         b.frame()
@@ -381,6 +383,16 @@ def test_frame_overlap_changes_no_bit():
     assert same(a.pixels.to_host(), b.pixels.to_host())
     assert reservoir_mismatch(a.output_reservoirs(), b.output_reservoirs()) == 0
     assert serial.shadow_rays_traced() == lapped.shadow_rays_traced()
+    assert same(a.visibility.to_host(), b.visibility.to_host())
+    # frames 2.. took their Visibility rows from the prefetch: one raycast launch per frame all the same (frames + 1 with the
+    # last prefetch), never two
+    assert lapped.launch_count() - launches[0] == serial.launch_count() - launches[1] + 1
+    # a camera the prefetch did not anticipate: the frame traces its own rays, the stale prefetch is dropped
+    a.set_camera((-0.3, 22.3, -6.4), (5.2, 20.8, 1.4))
+    b.set_camera((-0.3, 22.3, -6.4), (5.2, 20.8, 1.4))
+    a.frame()
+    b.frame()
+    assert same(a.visibility.to_host(), b.visibility.to_host()) and same(a.accumulation.to_host(), b.accumulation.to_host())
     assert float(a.accumulation.to_host().view(np.float32).reshape(-1, 4)[:, :3].sum()) > 0
     serial.close()
     lapped.close()
