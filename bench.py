@@ -323,6 +323,9 @@ def pixel_classes(torch, renderer):
 
 
 def run_cuda(args):
+    # each context drives up to three streams (frame, tail, prefetch) beside torch's and NCCL's: give them hardware queues of
+    # their own, so that a kernel of one stream is never queued behind another stream's (the default is 8 connections)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -549,7 +552,9 @@ def run_cuda(args):
             inst = ncu_warp_instructions(name) if comparable else None
             if inst:
                 k["warp_inst_per_launch"] = int(inst)
-                k["issue_frac"] = round(inst / (k["ms_per_launch"] * 1e-3) / issue_peak, 4)
+                # (clamped: for a 0.1 ms kernel the event-to-event time of the profile pass can come out a little shorter
+                # than its instructions allow at the sampled clock)
+                k["issue_frac"] = min(1.0, round(inst / (k["ms_per_launch"] * 1e-3) / issue_peak, 4))
         frame_ms_by_kernel = {k: v["ms_per_launch"] * v["launches_per_frame"] for k, v in kern.items()}
         dominant = max(frame_ms_by_kernel, key=frame_ms_by_kernel.get)
         passes = [k for k in kern if k in HBM_BOUND]

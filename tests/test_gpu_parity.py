@@ -558,7 +558,7 @@ def test_resolve_reuse_of_traced_visibility_changes_no_bit(rt):
     kw = dict(accumulate=1, use_temporal_resampling=1, use_spatial_resampling=1)
     os.environ["CRT_RESOLVE_REUSE"] = "0"
     try:
-        rt0 = cedecrt.Runtime(0)
+        rt0 = cedecrt.Runtime(0, rt.math_mode)  # the same arithmetic in both contexts (the library's default is REFERENCE)
     finally:
         del os.environ["CRT_RESOLVE_REUSE"]
     try:
