@@ -338,7 +338,9 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     # a real (non-default) torch stream: kernels, copies, NCCL and the timing events all go to it.  (The legacy
     # default stream's handle is 0, which crt_set_stream reads as "use the context's own stream".)
-    stream = torch.cuda.Stream()
+    # high priority: the frame's own kernel sequence is the critical path; the overlapped tail and the prefetched primary rays
+    # (the context's second and third streams, default priority) are there to fill what it leaves idle
+    stream = torch.cuda.Stream(priority=-1) if args.overlap else torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     # stdout carries exactly one JSON line: whatever libraries print while the run lasts (the image sets
     # NCCL_DEBUG=VERSION, so NCCL writes a version banner to file descriptor 1) goes to stderr instead

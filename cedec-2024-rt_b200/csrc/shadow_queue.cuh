@@ -41,6 +41,10 @@ struct ShadowQueue
 #define CRT_REFILL 24
 #endif
 constexpr int kRefillThreshold = CRT_REFILL;  // refetch when fewer lanes than this are still walking
+// Short queues (one GPU's slab of a multi-GPU frame) refill earlier: measured on a 3840x272 frame 0.245 -> 0.234 ms
+// (visibility reuse) and 0.295 -> 0.282 ms (resolve) at 28 against 24; at 4K 28 is no better (profiles/r2/tuning.txt)
+constexpr int kRefillThresholdShort = 28;
+constexpr uint32_t kShortQueue = 2000000u;
 
 #if defined(__CUDACC__)
 // warp-aggregated append; every lane of the warp must call it (has = whether this lane emits a ray)
@@ -170,6 +174,7 @@ template <int EPI>
 __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_trace_shadow_queue(Bvh bvh, ShadowQueue q, ShadowSink sink)
 {
     const uint32_t n_rays = *q.count;
+    const int refill_below = n_rays < kShortQueue ? kRefillThresholdShort : kRefillThreshold;
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.total + (EPI == kEpiResolve ? 1 : 0), (unsigned long long)n_rays);
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
             }
             act = __ballot_sync(full, active);
             if (act == 0) break;
-            if (!exhausted && __popc(act) < kRefillThreshold) break;
+            if (!exhausted && __popc(act) < refill_below) break;
         }
     }
 }
