@@ -82,6 +82,7 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
     if (ctx->queue_counters) cudaFree(ctx->queue_counters);
     if (ctx->gbuf) cudaFree(ctx->gbuf);
     if (ctx->inline_rays) cudaFree(ctx->inline_rays);
+    if (ctx->ao_count) cudaFree(ctx->ao_count);
     for (auto& m : ctx->prof_marks) cudaEventDestroy(m.second);
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);

@@ -23,6 +23,8 @@ struct crt_ctx
     void* queue_rays = nullptr;
     unsigned* queue_counters = nullptr;
     size_t queue_capacity = 0;
+    uint32_t* ao_count = nullptr;  // 06_ao as a wavefront: unoccluded AO rays per pixel
+    size_t ao_count_pixels = 0;
     unsigned long long* inline_rays = nullptr;  // {closest-hit, shadow / AO} rays traced by the single-kernel examples 06-09
     // frame overlap (crt_set_frame_overlap): the tail of the fused frame — the resolve rays and tone mapping — runs on a
     // second stream, so that the next frame's raycast and candidate kernels fill the tail's drain (and vice versa)

@@ -141,6 +141,79 @@ __global__ void __launch_bounds__(256, 3)  // 80 registers: the walk-step loop w
     if (t.in) pixels[t.px.idx] = px_ao<Math<MODE>>(t.px, raygen, W, H, bvh, tris60, n_rays, ao_rays);
     count_rays(ray_counters, t.in ? 1u : 0u, ao_rays);
 }
+// ---- 06_ao_hiprt.cu:35-91 as a wavefront (the shape the fused frame gives its shadow rays): the per-pixel kernel traces
+// the primary ray and only *emits* the n_rays hemisphere rays — compact 32-byte records, one queue reservation per warp,
+// ray i of the warp's hit pixels next to each other — the persistent kernel of shadow_queue.cuh walks them (t in
+// [0, FLT_MAX], near children first) and counts the unoccluded ones per pixel, and a third kernel turns the counts into
+// pixels.  Same rays, same random numbers, same counts as the single kernel (px_ao), which stays for CRT_WAVEFRONT=0.
+constexpr uint32_t kAoSky = 0xffffffffu;  // visible_count of a pixel whose primary ray missed
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    k_ao_emit(crt_raygen raygen, int W, int H, Rows rows, Bvh bvh, const float* tris60, int n_rays, ShadowQueue q,
+              uint32_t* visible_count, unsigned long long* ray_counters)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    const Pix px = t.px;
+    bool hit = false;
+    f3 n{0, 0, 0}, t0{0, 0, 0}, t1{0, 0, 0}, ao_ro{0, 0, 0};
+    Pcg rng(0, hash_pcg3(px.xi, px.yi, 42));
+    if (t.in)
+    {
+        f3 ro, rd;
+        primary_ray(raygen, px, W, H, ro, rd);
+        Hit h;
+        hit = trace<false>(bvh, ro, rd, 0.0f, kFltMax, h);
+        if (hit)
+        {
+            const TriRef tri = tri_at(tris60, h.prim);
+            const f3 v0 = tri.v(0), v1 = tri.v(1), v2 = tri.v(2);
+            n = tri_normal(v0, v1, v2);
+            if (0.0f < dot(n, rd)) n = -n;
+            t0 = normalize(v1 - v0);
+            t1 = cross(t0, n);
+            ao_ro = ro + rd * h.t + n * 0.0001f;
+        }
+        visible_count[px.idx] = hit ? 0u : kAoSky;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    count_rays(ray_counters, t.in ? 1u : 0u, hit ? (uint32_t)n_rays : 0u);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    const uint32_t n_hit = (uint32_t)__popc(mask), rank = (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(q.count, n_hit * (uint32_t)n_rays);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!hit) return;
+    float4* out = (float4*)q.rays;
+    for (int i = 0; i < n_rays; i++)
+    {
+        const float r0 = rng.next_f();
+        const float r1 = rng.next_f();
+        const float r2 = rng.next_f();
+        const f3 s = sample_hemisphere<Math<MODE>>(r0, r1, r2);
+        const f3 ao_rd = t0 * s.x + t1 * s.z + n * s.y;
+        float4* dst = out + ((size_t)base + (size_t)i * n_hit + rank) * 2;
+        dst[0] = make_float4(ao_ro.x, ao_ro.y, ao_ro.z, __uint_as_float((uint32_t)px.idx));
+        dst[1] = make_float4(ao_rd.x, ao_rd.y, ao_rd.z, 0.0f);
+    }
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ao_finish(size_t first, size_t n, uint32_t* pixels, const uint32_t* visible_count, int n_rays)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    {
+        const size_t i = first + k;
+        const uint32_t cnt = visible_count[i];
+        uint32_t c = 32u;  // background (06_ao_hiprt.cu:57-60)
+        if (cnt != kAoSky)
+        {
+            const float ao = (float)(int)cnt / (float)n_rays;
+            c = (uint32_t)(Math<MODE>::pow(ao, 1.0f / 2.2f) * 255.0f) & 0xffu;
+        }
+        pixels[i] = c | (c << 8) | (c << 16) | (255u << 24);
+    }
+}
+
 // the kernels of this file the fused frame launches (crt_slab_set_links loads them ahead of any spinning wait)
 int preload_dropin_kernels()
 {
@@ -485,8 +558,51 @@ extern "C" int crt_ao_06(crt_ctx* ctx, crt_buffer pixels, crt_raygen raygen, int
     CRT_REQUIRE(n_rays > 0, "n_rays must be positive");
     CRT_JOIN_TAIL(ctx);
     unsigned long long* counters = nullptr;
-    const int rc = inline_ray_counters(ctx, &counters);
+    int rc = inline_ray_counters(ctx, &counters);
     if (rc != CRT_OK) return rc;
+    if (ctx->wavefront)
+    {
+        // bands of rows, so that the ray queue of a band (pixels x n_rays x 32 B) stays below 4 GiB
+        const Rows all = rows_of(ctx, H);
+        const bool ex = ctx->math_mode == CRT_MATH_EXACT;
+        const size_t per_row = (size_t)W * (size_t)n_rays * 32u;
+        int band = (int)(((size_t)4 << 30) / (per_row ? per_row : 1));
+        band = band < kTileH ? kTileH : band / kTileH * kTileH;
+        if (ctx->ao_count_pixels < (size_t)W * H)
+        {
+            if (ctx->ao_count) CRT_CUDA(cudaFree(ctx->ao_count));
+            ctx->ao_count = nullptr;
+            ctx->ao_count_pixels = 0;
+            CRT_CUDA(cudaMalloc((void**)&ctx->ao_count, (size_t)W * H * sizeof(uint32_t)));
+            ctx->ao_count_pixels = (size_t)W * H;
+        }
+        for (int y0 = all.y0; y0 < all.y1; y0 += band)
+        {
+            const Rows rows{y0, y0 + band < all.y1 ? y0 + band : all.y1};
+            const size_t n_px = (size_t)(rows.y1 - rows.y0) * W, n_records = n_px * (size_t)n_rays;
+            CRT_REQUIRE(n_records < 0xffffffffull, "too many AO rays in one band");
+            ShadowQueue q{nullptr, nullptr, nullptr, 0};
+            rc = queue_prepare(ctx, (n_records + 1) / 2, &q);  // capacity is counted in 64-byte records
+            if (rc != CRT_OK) return rc;
+            q.tmax = kFltMax;  // the reference asks for the closest hit with maxT = FLT_MAX and only uses hit / no hit (:78-82)
+            q.stride4 = 2;
+            (ex ? k_ao_emit<1> : k_ao_emit<0>)<<<tile_grid(W, rows), 256, 0, ctx->stream>>>(raygen, W, H, rows, geom->view(),
+                                                                                         (const float*)triangles.data, n_rays, q,
+                                                                                         ctx->ao_count, counters);
+            rc = check_launch(ctx, "ao_emit");
+            if (rc != CRT_OK) return rc;
+            ShadowSink sink{nullptr, nullptr, 0, nullptr};
+            sink.visible_count = ctx->ao_count;
+            rc = queue_trace<kEpiCountVisible>(ctx, geom, q, sink);
+            if (rc != CRT_OK) return rc;
+            const size_t first = (size_t)(H - rows.y1) * W;
+            (ex ? k_ao_finish<1> : k_ao_finish<0>)<<<sweep_blocks(ctx, n_px), 256, 0, ctx->stream>>>(first, n_px, (uint32_t*)pixels.data,
+                                                                                                   ctx->ao_count, n_rays);
+            rc = check_launch(ctx, "ao_finish");
+            if (rc != CRT_OK) return rc;
+        }
+        return CRT_OK;
+    }
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_ao<1> : k_ao<0>;
     k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>((uint32_t*)pixels.data, raygen, W, H, rows_of(ctx, H), geom->view(),
                                                (const float*)triangles.data, n_rays, counters);

@@ -107,7 +107,7 @@ static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, co
     }
     cudaStream_t st = on ? on : ctx->stream;
     k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, st>>>(geom->view(), q, sink);
-    return check_launch(ctx, (EPI == kEpiReservoirVisibility || EPI == kEpiSoaVisibility) ? "trace_visibility_reuse" : "trace_resolve", st);
+    return check_launch(ctx, EPI == kEpiCountVisible ? "trace_ao" : (EPI == kEpiReservoirVisibility || EPI == kEpiSoaVisibility) ? "trace_visibility_reuse" : "trace_resolve", st);
 }
 // light records for (geometry, light list); rebuilt when another list is passed
 static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60, const uint32_t* lights, size_t n,

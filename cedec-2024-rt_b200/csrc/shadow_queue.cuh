@@ -35,6 +35,8 @@ struct ShadowQueue
     uint32_t* next;    // next ray to fetch (persistent kernel)
     uint32_t capacity;
     unsigned long long* total;  // rays traced since crt_init: [0] visibility reuse, [1] resolve (crt_shadow_rays_traced)
+    float tmax = 0.99f;         // the segment is t in [0, tmax]: 0.99 for check_visibility (raytrace.hpp:45-52), FLT_MAX for AO rays
+    uint32_t stride4 = 4;       // record size in 16-byte words: 4 = ShadowRay, 2 = compact (origin + pixel, direction) for AO rays
 };
 
 #ifndef CRT_REFILL
@@ -72,7 +74,8 @@ enum
 {
     kEpiReservoirVisibility = 0,  // reservoirs[pix].sample.visibility = !occluded   (generate_candidate, AoS)
     kEpiResolve = 1,              // accumulation[pix] (+)= brdf*G*V*radiance*ucw     (resolve)
-    kEpiSoaVisibility = 2         // fused frame: set the visibility bit of the reservoir record (restir_fast.cuh)
+    kEpiSoaVisibility = 2,        // fused frame: set the visibility bit of the reservoir record (restir_fast.cuh)
+    kEpiCountVisible = 3          // 06_ao: visible_count[pix] += 1 for an unoccluded ray (06_ao_hiprt.cu:78-82)
 };
 
 struct ShadowSink
@@ -86,6 +89,7 @@ struct ShadowSink
     uint32_t* up_plane0 = nullptr;
     uint32_t* down_plane0 = nullptr;
     uint32_t up_first_idx = 0, down_end_idx = 0;
+    uint32_t* visible_count = nullptr;  // kEpiCountVisible
 };
 
 // the shading factors stay in the queue record until the ray is decided (keeps the walk's register count down)
@@ -93,7 +97,11 @@ template <int EPI>
 __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const ShadowRay* rec, uint32_t pix,
                                                 bool occluded)
 {
-    if (EPI == kEpiReservoirVisibility)
+    if (EPI == kEpiCountVisible)
+    {
+        if (!occluded) atomicAdd(sink.visible_count + pix, 1u);
+    }
+    else if (EPI == kEpiReservoirVisibility)
     {
         // word 15 of the 19-word Reservoir holds `bool visibility` (+ 3 padding bytes)
         ((uint32_t*)(sink.reservoirs + pix))[15] = occluded ? 0u : 1u;
@@ -124,7 +132,7 @@ __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const Sh
 
 // One node step of the any-hit walk (the node half of walk_step): pops / descends and leaves the hit
 // triangles of the visited node in w.tmask.  Returns false when the walk has nothing left (a miss).
-__device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, WalkStack& st, const RaySetup& r)
+__device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, WalkStack& st, const RaySetup& r, float tmax)
 {
     if ((w.ng_mask >> 24) == 0)
     {
@@ -144,7 +152,7 @@ __device__ __forceinline__ bool shadow_node_step(const Bvh& bvh, Walk& w, WalkSt
         ++w.sp;
     }
     uint32_t imask;
-    const uint32_t hits = intersect_node(bvh, node_idx, r, 0.0f, 0.99f, w.ng_base, w.tri_base, imask);
+    const uint32_t hits = intersect_node(bvh, node_idx, r, 0.0f, tmax, w.ng_base, w.tri_base, imask);
     w.ng_mask = (hits & 0xff000000u) | imask;
     w.tmask = hits & 0x00ffffffu;
     return true;
@@ -177,7 +185,9 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
     const int refill_below = n_rays < kShortQueue ? kRefillThresholdShort : kRefillThreshold;
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.total + (EPI == kEpiResolve ? 1 : 0), (unsigned long long)n_rays);
+    if (EPI != kEpiCountVisible && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(q.total + (EPI == kEpiResolve ? 1 : 0), (unsigned long long)n_rays);
+    const float tmax = q.tmax;
 
     bool active = false, exhausted = false;
     RaySetup r;
@@ -205,14 +215,14 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                     const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
                     if (my < n_rays)
                     {
-                        const float4* src = (const float4*)(q.rays + my);
+                        const float4* src = (const float4*)q.rays + (size_t)my * q.stride4;
                         const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
                         pix = __float_as_uint(w0.w);
                         ray_idx = my;
                         // visibility-reuse rays aim at freshly sampled lights: 93 % are occluded, mostly next to the light, so
                         // their walk starts at the far end (bvh.cuh: setup_ray); resolve rays aim at samples that survived
                         // the resampling — three quarters are clear, and for the rest the near end finds the blocker sooner
-                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z}, EPI != kEpiResolve);
+                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z}, EPI == kEpiSoaVisibility || EPI == kEpiReservoirVisibility);
                         walk_begin(w, r);
                         active = true;
                     }
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
         {
             // node phase
             bool missed = false;
-            if (active) missed = !shadow_node_step(bvh, w, stack, r);
+            if (active) missed = !shadow_node_step(bvh, w, stack, r, tmax);
             // triangle phase: inclusive scan of the per-lane pair counts
             const uint32_t own_mask = active ? w.tmask : 0u;
             const uint32_t cnt = (uint32_t)__popc(own_mask);
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                     }
                     Hit h;
                     h.prim = -1;
-                    h.t = 0.99f;
+                    h.t = tmax;
                     h.u = h.v = 0.0f;
                     hit = intersect_wide_tri(bvh.tris + tri_base + shift, o, 0.0f, h);  // bit `shift` of m is that triangle
                 }
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
             w.tmask = 0;
             if (active && (occluded || missed))
             {
-                shadow_epilogue<EPI>(sink, q.rays + ray_idx, pix, occluded);
+                shadow_epilogue<EPI>(sink, (const ShadowRay*)((const float4*)q.rays + (size_t)ray_idx * q.stride4), pix, occluded);
                 active = false;
             }
             act = __ballot_sync(full, active);
