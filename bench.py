@@ -772,13 +772,15 @@ def run_example(args):
         per = {}
         for name, t_ms in marks:
             per.setdefault(name, []).append(t_ms)
-        kern = {k: {"ms_per_launch": round(sum(v) / len(v), 4)} for k, v in per.items()}
+        kern = {k: {"ms_per_launch": round(sum(v) / len(v), 4), "launches_per_frame": len(v) / 2, "ms_per_frame": round(sum(v) / 2, 4)}
+                for k, v in per.items()}
         sm_count = torch.cuda.get_device_properties(local).multi_processor_count
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = sm_count * 4 * sm_mhz * 1e6
-        main_name = max(kern, key=lambda k: kern[k]["ms_per_launch"])  # the dominant kernel of the frame
+        main_name = max(kern, key=lambda k: kern[k]["ms_per_frame"])  # the dominant kernel of the frame
         ncu_name = {"ao_emit": "k_ao_emit", "trace_ao": "k_trace_shadow_queue<3>", "ao_finish": "k_ao_finish", "ao_06": "k_ao<",
-                    "path_trace": ex["ncu"]}.get(main_name, main_name)
+                    "path_trace": ex["ncu"], "trace_shadow": "k_trace_shadow_queue<4>", "pt_closest": "k_pt_closest",
+                    "pt_vertex": "k_pt_vertex", "pt_replay": "k_pt_replay", "pt_shade_bounce": "k_pt_shade_bounce"}.get(main_name, main_name)
         inst = ncu_warp_instructions(ncu_name) if world == 1 and (W, H) == (1920, 1080) else None
         roof = {"kernel": main_name, "bound": "issue", "unit": "Gwarp-inst/s", "peak": round(issue_peak / 1e9, 2),
                 "achieved": None, "frac": None, "traffic": None,

@@ -83,6 +83,7 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
     if (ctx->gbuf) cudaFree(ctx->gbuf);
     if (ctx->inline_rays) cudaFree(ctx->inline_rays);
     if (ctx->ao_count) cudaFree(ctx->ao_count);
+    if (ctx->path_state) cudaFree(ctx->path_state);
     for (auto& m : ctx->prof_marks) cudaEventDestroy(m.second);
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);

@@ -23,6 +23,8 @@ struct crt_ctx
     void* queue_rays = nullptr;
     unsigned* queue_counters = nullptr;
     size_t queue_capacity = 0;
+    void* path_state = nullptr;  // examples 07-09 as a wavefront: per-path state (kernels_paths.cu)
+    size_t path_state_pixels = 0;
     uint32_t* ao_count = nullptr;  // 06_ao as a wavefront: unoccluded AO rays per pixel
     size_t ao_count_pixels = 0;
     unsigned long long* inline_rays = nullptr;  // {closest-hit, shadow / AO} rays traced by the single-kernel examples 06-09

@@ -526,6 +526,11 @@ static int path_trace(crt_ctx* ctx, int W, int H, int frame, crt_geometry geom, 
     unsigned long long* counters = nullptr;
     const int rc = inline_ray_counters(ctx, &counters);
     if (rc != CRT_OK) return rc;
+    // the wavefront form (kernels_paths.cu) packs path | ray << 27 into a record word and keeps a 32-bit visibility mask per vertex
+    const bool wave_ok = (size_t)W * H < ((size_t)1 << 27) && (!options.use_shadowed_target_function || options.ris_sample_count <= 32);
+    if (ctx->wavefront && wave_ok)
+        return path_trace_wavefront(ctx, EX, W, H, frame, geom, (const float*)triangles.data, (const uint32_t*)lights.data,
+                                    (uint32_t)bsize(lights), raygen, options, (crt_float4*)accumulation.data, counters);
     auto k = ctx->math_mode == CRT_MATH_EXACT ? k_path_trace<EX, 1> : k_path_trace<EX, 0>;
     k<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), frame, geom->view(), (const float*)triangles.data,
                                                (const uint32_t*)lights.data, (uint32_t)bsize(lights), raygen, options,

@@ -107,7 +107,7 @@ static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, co
     }
     cudaStream_t st = on ? on : ctx->stream;
     k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, st>>>(geom->view(), q, sink);
-    return check_launch(ctx, EPI == kEpiCountVisible ? "trace_ao" : (EPI == kEpiReservoirVisibility || EPI == kEpiSoaVisibility) ? "trace_visibility_reuse" : "trace_resolve", st);
+    return check_launch(ctx, EPI == kEpiCountVisible ? "trace_ao" : EPI == kEpiBitmask ? "trace_shadow" : (EPI == kEpiReservoirVisibility || EPI == kEpiSoaVisibility) ? "trace_visibility_reuse" : "trace_resolve", st);
 }
 // light records for (geometry, light list); rebuilt when another list is passed
 static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60, const uint32_t* lights, size_t n,
@@ -135,6 +135,9 @@ static int light_table_for(crt_ctx* ctx, crt_geometry geom, const float* tris60,
 namespace crt
 {
 // force the (lazily loaded) kernels of a translation unit into the context; see crt_slab_set_links
+int path_trace_wavefront(crt_ctx* ctx, int example, int W, int H, int frame, crt_geometry geom, const float* tris60,
+                         const uint32_t* lights, uint32_t n_lights, crt_raygen raygen, crt_options options, crt_float4* accum,
+                         unsigned long long* counters);
 int raycast_or_prefetched(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_raygen raygen, crt_buffer visibility);
 int tone_mapping_on(crt_ctx* ctx, cudaStream_t st, crt_buffer pixels, crt_buffer accumulation, int W, int H);
 int preload_fused_kernels();

@@ -75,7 +75,9 @@ enum
     kEpiReservoirVisibility = 0,  // reservoirs[pix].sample.visibility = !occluded   (generate_candidate, AoS)
     kEpiResolve = 1,              // accumulation[pix] (+)= brdf*G*V*radiance*ucw     (resolve)
     kEpiSoaVisibility = 2,        // fused frame: set the visibility bit of the reservoir record (restir_fast.cuh)
-    kEpiCountVisible = 3          // 06_ao: visible_count[pix] += 1 for an unoccluded ray (06_ao_hiprt.cu:78-82)
+    kEpiCountVisible = 3,         // 06_ao: visible_count[pix] += 1 for an unoccluded ray (06_ao_hiprt.cu:78-82)
+    kEpiBitmask = 4               // 08_nee / 09_ris (kernels_paths.cu): the record's word packs path | ray << 27; bit `ray` of
+                                  // visible_count[path] is set for an unoccluded ray
 };
 
 struct ShadowSink
@@ -100,6 +102,10 @@ __device__ __forceinline__ void shadow_epilogue(const ShadowSink& sink, const Sh
     if (EPI == kEpiCountVisible)
     {
         if (!occluded) atomicAdd(sink.visible_count + pix, 1u);
+    }
+    else if (EPI == kEpiBitmask)
+    {
+        if (!occluded) atomicOr(sink.visible_count + (pix & 0x07ffffffu), 1u << (pix >> 27));
     }
     else if (EPI == kEpiReservoirVisibility)
     {
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
     const int refill_below = n_rays < kShortQueue ? kRefillThresholdShort : kRefillThreshold;
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    if (EPI != kEpiCountVisible && blockIdx.x == 0 && threadIdx.x == 0)
+    if (EPI != kEpiCountVisible && EPI != kEpiBitmask && blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(q.total + (EPI == kEpiResolve ? 1 : 0), (unsigned long long)n_rays);
     const float tmax = q.tmax;
 
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                         // visibility-reuse rays aim at freshly sampled lights: 93 % are occluded, mostly next to the light, so
                         // their walk starts at the far end (bvh.cuh: setup_ray); resolve rays aim at samples that survived
                         // the resampling — three quarters are clear, and for the rest the near end finds the blocker sooner
-                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z}, EPI == kEpiSoaVisibility || EPI == kEpiReservoirVisibility);
+                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z}, EPI == kEpiSoaVisibility || EPI == kEpiReservoirVisibility || EPI == kEpiBitmask);
                         walk_begin(w, r);
                         active = true;
                     }
