@@ -50,6 +50,7 @@ extern "C" int crt_init(int device, crt_ctx** out)
     if (const char* e = getenv("CRT_WAVEFRONT")) ctx->wavefront = atoi(e);
     if (const char* e = getenv("CRT_LIGHT_TABLE")) ctx->light_table = atoi(e);
     if (const char* e = getenv("CRT_RESOLVE_REUSE")) ctx->resolve_reuse = atoi(e);
+    if (const char* e = getenv("CRT_POOLED_CLOSEST")) ctx->pooled_closest = atoi(e);
     *out = ctx;
     return CRT_OK;
 }

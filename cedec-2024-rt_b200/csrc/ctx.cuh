@@ -23,6 +23,7 @@ struct crt_ctx
     void* queue_rays = nullptr;
     unsigned* queue_counters = nullptr;
     size_t queue_capacity = 0;
+    int pooled_closest = 1;  // examples 07-09: closest hits through the persistent pooled kernel (CRT_POOLED_CLOSEST: 0 never, 1 bounce rays, 2 all)
     void* path_state = nullptr;  // examples 07-09 as a wavefront: per-path state (kernels_paths.cu)
     size_t path_state_pixels = 0;
     uint32_t* ao_count = nullptr;  // 06_ao as a wavefront: unoccluded AO rays per pixel

@@ -5,7 +5,8 @@
 // (profiles/r2/ncu_r2_cfg_summary.csv): lanes wait for the longest walk of every ray, and 09_ris with the shadowed target
 // function walks 33 shadow rays per path vertex one after the other.  Here a frame is, per path depth,
 //
-//   k_pt_closest        the closest hit of every live path's ray (per-thread walk, rays of one depth only)
+//   k_pt_emit_closest + k_trace_closest_queue   the closest hit of every live path's ray: ray records and the persistent
+//                       pooled closest-hit kernel of shadow_queue.cuh (k_pt_closest, the per-thread walk, with CRT_POOLED_CLOSEST=0)
 //   k_pt_vertex         miss / emitter / surface; light sampling; the shadow rays are only *emitted*: compact 32-byte
 //                       records, one queue reservation per warp, ray c of the warp's paths next to each other
 //   k_trace_shadow_queue<kEpiBitmask>   the persistent any-hit kernel of shadow_queue.cuh: bit c of the path's mask = ray c
@@ -88,6 +89,36 @@ __global__ void __launch_bounds__(256)
     }
     const uint32_t c = __reduce_add_sync(0xffffffffu, traced ? 1u : 0u);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(ray_counters + 0, (unsigned long long)c);
+}
+
+// the live paths' rays as queue records for k_trace_closest_queue (shadow_queue.cuh)
+__global__ void __launch_bounds__(256)
+    k_pt_emit_closest(int W, int H, Rows rows, PathState st, ShadowQueue q, unsigned long long* ray_counters)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    const int idx = t.px.idx;
+    float4 rdp = make_float4(0, 0, 0, 0);
+    bool live = false;
+    if (t.in)
+    {
+        rdp = st.rd_prim[idx];
+        live = __float_as_int(rdp.w) != kPathDead;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader)
+    {
+        base = atomicAdd(q.count, (uint32_t)__popc(mask));
+        atomicAdd(ray_counters + 0, (unsigned long long)__popc(mask));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!live) return;
+    const float4 rot = st.ro_t[idx];
+    float4* dst = (float4*)q.rays + ((size_t)base + (size_t)__popc(mask & ((1u << lane) - 1u))) * 2;
+    dst[0] = make_float4(rot.x, rot.y, rot.z, __uint_as_float((uint32_t)idx));
+    dst[1] = make_float4(rdp.x, rdp.y, rdp.z, 0.0f);
 }
 
 // compact ray record of path `pix`, ray `c` of its vertex (the tracer's kEpiBitmask epilogue sets bit c)
@@ -383,10 +414,33 @@ static int path_trace_wavefront_impl(crt_ctx* ctx, int W, int H, int frame, crt_
         rc = check_launch(ctx, "pt_begin");
         for (int depth = 0; rc == CRT_OK && depth < options.max_depth; ++depth)
         {
-            k_pt_closest<<<grid, 256, 0, ctx->stream>>>(W, H, rows, bvh, st, counters);
-            rc = check_launch(ctx, "pt_closest");
-            if (rc != CRT_OK) break;
             ShadowQueue q{nullptr, nullptr, nullptr, 0};
+            // closest hits: the persistent pooled kernel for the incoherent bounce rays, the per-thread walk for the coherent
+            // camera rays (08_nee at 1080p: 2.74 ms per frame; pooled for every depth 2.88; per-thread for every depth 3.61 —
+            // profiles/r2/tuning.txt).  CRT_POOLED_CLOSEST = 0 never / 1 bounce rays (default) / 2 always
+            if (ctx->pooled_closest >= (depth == 0 ? 2 : 1))
+            {
+                rc = queue_prepare(ctx, (n_px + 1) / 2, &q);
+                if (rc != CRT_OK) break;
+                q.stride4 = 2;
+                k_pt_emit_closest<<<grid, 256, 0, ctx->stream>>>(W, H, rows, st, q, counters);
+                rc = check_launch(ctx, "pt_emit_closest");
+                if (rc != CRT_OK) break;
+                static int closest_blocks = 0;
+                if (!closest_blocks)
+                {
+                    CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&closest_blocks, k_trace_closest_queue, kShadowWarps * 32, 0));
+                    if (closest_blocks < 1) closest_blocks = 1;
+                }
+                k_trace_closest_queue<<<closest_blocks * ctx->sm_count, kShadowWarps * 32, 0, ctx->stream>>>(bvh, q, ClosestSink{st.ro_t, st.rd_prim});
+                rc = check_launch(ctx, "trace_closest");
+            }
+            else
+            {
+                k_pt_closest<<<grid, 256, 0, ctx->stream>>>(W, H, rows, bvh, st, counters);
+                rc = check_launch(ctx, "pt_closest");
+            }
+            if (rc != CRT_OK) break;
             if (EX != 7)
             {
                 rc = queue_prepare(ctx, (n_px * (rays_per_px ? rays_per_px : 1) + 1) / 2, &q);  // capacity in 64-byte records

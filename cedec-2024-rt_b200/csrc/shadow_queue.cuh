@@ -323,5 +323,176 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
         }
     }
 }
+
+// ---- the same persistent kernel for CLOSEST hits (kernels_paths.cu: the camera and bounce rays of examples 07-09, whose
+// per-thread walk ran at 7 lanes per instruction).  Records are the compact 32-byte form (origin + path, direction); the
+// segment is t in [0, FLT_MAX].  Differences from the any-hit kernel: the node phase culls with the lane's current best t,
+// children near the origin first; in the triangle phase every (ray, triangle) pair is tested against the best hit its
+// owner had when the round began, and the owner then takes the best of the pairs that beat it — smallest t, then largest
+// primitive id, the order of the reference's exhaustive loop (04_ao.cu:14-24), which does not depend on the order of the
+// tests — so the result is the per-thread walk's, bit for bit.  The hit goes to the path state of kernels_paths.cu.
+struct ClosestSink
+{
+    float4* ro_t;     // .w <- hit distance
+    float4* rd_prim;  // .w <- primitive id (int bits), -1 for a miss
+};
+#ifndef CRT_CLOSEST_MINBLOCKS
+#define CRT_CLOSEST_MINBLOCKS 6
+#endif
+static __global__ void __launch_bounds__(kShadowWarps * 32, CRT_CLOSEST_MINBLOCKS) k_trace_closest_queue(Bvh bvh, ShadowQueue q, ClosestSink sink)
+{
+    const uint32_t n_rays = *q.count;
+    const int refill_below = n_rays < kShortQueue ? kRefillThresholdShort : kRefillThreshold;
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+
+    bool active = false, exhausted = false;
+    RaySetup r;
+    r.ro = r.rd = f3{0.0f, 0.0f, 0.0f};
+    uint32_t pix = 0;
+    Walk w;
+    WalkStack stack;
+    w.sp = 0;
+    w.ng_base = w.ng_mask = w.tri_base = w.tmask = 0;
+    Hit best;
+    best.t = kFltMax;
+    best.u = best.v = 0.0f;
+    best.prim = -1;
+
+    for (;;)
+    {
+        if (!exhausted)
+        {
+            const unsigned idle = __ballot_sync(full, !active);
+            if (idle)
+            {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(q.next, (uint32_t)__popc(idle));
+                base = __shfl_sync(full, base, leader);
+                if (!active)
+                {
+                    const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                    if (my < n_rays)
+                    {
+                        const float4* src = (const float4*)q.rays + (size_t)my * 2;
+                        const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
+                        pix = __float_as_uint(w0.w);
+                        r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z});
+                        walk_begin(w, r);
+                        best.t = kFltMax;
+                        best.u = best.v = 0.0f;
+                        best.prim = -1;
+                        active = true;
+                    }
+                }
+                if (base + (uint32_t)__popc(idle) >= n_rays) exhausted = true;  // warp-uniform
+            }
+        }
+        unsigned act = __ballot_sync(full, active);
+        if (act == 0) break;
+
+        for (;;)
+        {
+            // node phase: one node step per walking lane, culled by its best hit so far
+            bool finished = false;
+            if (active) finished = !shadow_node_step(bvh, w, stack, r, best.t);
+            // triangle phase: the warp's (ray, triangle) pairs dealt out over its lanes (see k_trace_shadow_queue)
+            const uint32_t own_mask = active ? w.tmask : 0u;
+            const uint32_t cnt = (uint32_t)__popc(own_mask);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t v = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t total = __shfl_sync(full, incl, 31);
+            const uint32_t excl = incl - cnt;
+            for (uint32_t base = 0; base < total; base += 32)
+            {
+                const uint32_t g = base + (uint32_t)lane;
+                int owner = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1)
+                {
+                    const uint32_t v = __shfl_sync(full, incl, owner + step - 1);
+                    if (v <= g) owner += step;
+                }
+                const bool valid = g < total;
+                const uint32_t first = __shfl_sync(full, excl, owner);
+                const uint32_t m = __shfl_sync(full, own_mask, owner);
+                const uint32_t tri_base = __shfl_sync(full, w.tri_base, owner);
+                RaySetup o;
+                o.ro.x = __shfl_sync(full, r.ro.x, owner);
+                o.ro.y = __shfl_sync(full, r.ro.y, owner);
+                o.ro.z = __shfl_sync(full, r.ro.z, owner);
+                o.rd.x = __shfl_sync(full, r.rd.x, owner);
+                o.rd.y = __shfl_sync(full, r.rd.y, owner);
+                o.rd.z = __shfl_sync(full, r.rd.z, owner);
+                Hit h;  // the owner's best hit as the round begins: a pair only reports a hit that beats it
+                h.t = __shfl_sync(full, best.t, owner);
+                h.prim = __shfl_sync(full, best.prim, owner);
+                h.u = h.v = 0.0f;
+                bool hit = false;
+                if (valid)
+                {
+                    uint32_t k = g - first, shift = 0;
+#pragma unroll
+                    for (int width = 16; width; width >>= 1)
+                    {
+                        const uint32_t c = (uint32_t)__popc((m >> shift) & ((1u << width) - 1u));
+                        if (k >= c)
+                        {
+                            k -= c;
+                            shift += (uint32_t)width;
+                        }
+                    }
+                    hit = intersect_wide_tri(bvh.tris + tri_base + shift, o, 0.0f, h);
+                }
+                // the owner scans the lanes that tested its pairs in this round, [lo, hi), for the best of their hits:
+                // smallest t, then largest primitive id.  (t >= 0 here, and -0 is folded into +0 for the comparison only.)
+                const int lo = (int)excl - (int)base, hi = (int)incl - (int)base;
+                const int seg_lo = lo < 0 ? 0 : lo, seg_hi = hi > 32 ? 32 : hi;
+                const int seg = seg_hi > seg_lo ? seg_hi - seg_lo : 0;
+                const int longest = __reduce_max_sync(full, seg);
+                const uint32_t key_t = hit ? __float_as_uint(h.t + 0.0f) : 0xffffffffu;
+                const uint32_t key_p = hit ? (uint32_t)h.prim : 0u;
+                uint32_t win_t = 0xffffffffu, win_p = 0u;
+                int win_lane = -1;
+                for (int it = 0; it < longest; ++it)
+                {
+                    const int src = seg_lo + it < 32 ? seg_lo + it : 31;
+                    const uint32_t kt = __shfl_sync(full, key_t, src), kp = __shfl_sync(full, key_p, src);
+                    if (it < seg && (kt < win_t || (kt == win_t && kt != 0xffffffffu && kp > win_p)))
+                    {
+                        win_t = kt;
+                        win_p = kp;
+                        win_lane = src;
+                    }
+                }
+                const int from = win_lane >= 0 ? win_lane : lane;
+                const float wt = __shfl_sync(full, h.t, from), wu = __shfl_sync(full, h.u, from), wv = __shfl_sync(full, h.v, from);
+                if (win_lane >= 0)
+                {
+                    best.t = wt;
+                    best.u = wu;
+                    best.v = wv;
+                    best.prim = (int)win_p;
+                }
+            }
+            w.tmask = 0;
+            if (active && finished)
+            {
+                sink.ro_t[pix].w = best.t;
+                sink.rd_prim[pix].w = __int_as_float(best.prim);
+                active = false;
+            }
+            act = __ballot_sync(full, active);
+            if (act == 0) break;
+            if (!exhausted && __popc(act) < refill_below) break;
+        }
+    }
+}
 #endif  // __CUDACC__
 }  // namespace crt
