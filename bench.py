@@ -408,6 +408,7 @@ def run_cuda(args):
     barrier()
     launches0 = r.launch_count()
     rays0 = r.shadow_rays_traced()
+    decided0 = r.rays_decided_at_emission()[0]
     sampler.mark_begin()
     # ---- timed: K frames, resident buffers
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -422,6 +423,7 @@ def run_cuda(args):
     launches = r.launch_count() - launches0
     rays1 = r.shadow_rays_traced()
     shadow_rays = [(b - a) / args.steps for a, b in zip(rays0, rays1)]  # per frame: (visibility reuse, resolve)
+    decided_vr = (r.rays_decided_at_emission()[0] - decided0) / args.steps  # this rank's, settled by the own-triangle pre-test
     # ---- timed: K frames end to end (per-frame D2H of the RGBA8 image into pinned host memory)
     if args.readback == "pipelined":
         r.wait_download(r.download_pixels_async())  # allocates the copy stream and the pinned images, untimed
@@ -590,10 +592,13 @@ def run_cuda(args):
             "grays_per_s": round(rays * args.steps / ms / 1e6, 4), "rays_per_frame": int(rays),
             "rays": {"primary": int(all_px), "visibility_reuse": int(rays_vr), "resolve": int(rays_rs),
                      "reference_would_trace": int(all_px + 2 * all_diffuse),
+                     "visibility_reuse_decided_at_emission_rank0": int(decided_vr),
                      "note": "per frame, counted by the tracer (crt_shadow_rays_traced); the reference traces one "
                              "visibility-reuse and one resolve ray per diffuse pixel, the fused frame omits those "
                              "whose outcome cannot be read (candidate lost the temporal merge) or is already known "
-                             "(resolve ray identical to a traced visibility-reuse ray)"},
+                             "(resolve ray identical to a traced visibility-reuse ray), and settles a visibility-reuse "
+                             "ray without a walk when the triangle it starts on stops it (crt_rays_decided_at_emission; "
+                             "not counted in grays_per_s)"},
             "e2e": {"value": round(n_img * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s",
                     "h2d_bytes_per_step": 96, "d2h_bytes_per_step": 4 * n_img,
                     "readback": args.readback,
@@ -728,6 +733,7 @@ def run_example(args):
         frame()
     barrier()
     launches0, rays0 = rt.launch_count(), rt.inline_rays_traced()
+    decided0 = rt.rays_decided_at_emission()[1]
     sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -739,6 +745,7 @@ def run_example(args):
     ms = e0.elapsed_time(e1)
     launches, rays1 = rt.launch_count() - launches0, rt.inline_rays_traced()
     rays = [(b - a) / args.steps for a, b in zip(rays0, rays1)]
+    decided = (rt.rays_decided_at_emission()[1] - decided0) / args.steps
     # end to end: the frame plus the device -> host copy of this rank's RGBA8 rows and a stream synchronise
     # (06_ao_hiprt.cpp / 08_nee.cpp / 09_ris.cpp read back and display every frame)
     rows_px = t_pix[(H - y1) * W * 4:(H - y0) * W * 4]
@@ -800,8 +807,10 @@ def run_example(args):
                              "blocks_ao, larger than L2 for blocks_pt / blocks_restir" % ((stats["node_bytes"] + stats["tri_bytes"]) // 2**20),
                        "math": "libdevice functions, uncontracted arithmetic (the per-kernel entry points' default)"},
             "grays_per_s": round(sum(rays) * args.steps / ms / 1e6, 4), "rays_per_frame": int(sum(rays)),
-            "rays": {"closest_hit": int(rays[0]), "shadow_or_ao": int(rays[1]),
-                     "note": "per frame, counted by the kernel itself (crt_inline_rays_traced), SURVEY.md section 8d accounting"},
+            "rays": {"closest_hit": int(rays[0]), "shadow_or_ao": int(rays[1]), "shadow_decided_at_emission": int(decided),
+                     "note": "per frame, counted by the kernel itself (crt_inline_rays_traced), SURVEY.md section 8d accounting; "
+                             "shadow rays that the triangle they start on stops are settled by the emitting kernel without a walk "
+                             "(crt_rays_decided_at_emission) and are not counted in grays_per_s"},
             "e2e": {"value": round(n * args.steps / ms_e2e / 1e3, 3), "unit": "Mpix/s", "h2d_bytes_per_step": 132,
                     "d2h_bytes_per_step": 4 * n, "note": "frame + RGBA8 device->host copy into pinned memory + stream synchronise"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kern,

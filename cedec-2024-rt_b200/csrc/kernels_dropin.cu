@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256)
     const TilePix t = this_pixel(W, H, rows);
     DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
     if (t.in) d = px_generate_candidate(t.px, frame, bvh, tris60, vis, eye, lights, kernel_opt<SH>(options), AosStore{out}, WF);
-    if (WF) queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
+    if (WF) queue_push(q, d.want, to_shadow_ray(d, t.px.idx), d.decided);
 }
 template <int MODE, bool SH>
 __global__ void __launch_bounds__(256)
@@ -497,8 +497,8 @@ static int inline_ray_counters(crt_ctx* ctx, unsigned long long** out)
 {
     if (!ctx->inline_rays)
     {
-        CRT_CUDA(cudaMalloc((void**)&ctx->inline_rays, 2 * sizeof(unsigned long long)));
-        CRT_CUDA(cudaMemsetAsync(ctx->inline_rays, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CRT_CUDA(cudaMalloc((void**)&ctx->inline_rays, 3 * sizeof(unsigned long long)));  // [2]: settled by the own-triangle pre-test
+        CRT_CUDA(cudaMemsetAsync(ctx->inline_rays, 0, 3 * sizeof(unsigned long long), ctx->stream));
     }
     *out = ctx->inline_rays;
     return CRT_OK;
@@ -509,6 +509,17 @@ extern "C" int crt_inline_rays_traced(crt_ctx* ctx, unsigned long long out[2])
     out[0] = out[1] = 0;
     if (!ctx->inline_rays) return CRT_OK;
     CRT_CUDA(cudaMemcpyAsync(out, ctx->inline_rays, 2 * sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CRT_OK;
+}
+
+extern "C" int crt_rays_decided_at_emission(crt_ctx* ctx, unsigned long long out[2])
+{
+    CRT_REQUIRE(ctx && out, "null argument");
+    CRT_JOIN_TAIL(ctx);
+    out[0] = out[1] = 0;
+    if (ctx->queue_counters) CRT_CUDA(cudaMemcpyAsync(out, ctx->queue_counters + 6, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->inline_rays) CRT_CUDA(cudaMemcpyAsync(out + 1, ctx->inline_rays + 2, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
     CRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRT_OK;
 }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
     // lanes 2k, 2k+1 are horizontal neighbours of the warp's 8x4 tile: they share their light-record gathers
     const unsigned pairs = complete_pairs(__ballot_sync(0xffffffffu, t.in && !cp.skip));
     if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, cp, frame, bvh, tris60, eye, lights, make_opt(options), temporal, g, peers, pairs);
-    queue_push(q, d.want, to_shadow_ray(d, t.px.idx));
+    queue_push(q, d.want, to_shadow_ray(d, t.px.idx), d.decided);
 }
 #ifndef CRT_SP_MINBLOCKS
 #define CRT_SP_MINBLOCKS 4  // 64 registers: 0.83 -> 0.75 ms per pass against 3 (profiles/r1/tuning_q.txt)

@@ -128,6 +128,20 @@ __device__ __forceinline__ void put_ray(const ShadowQueue& q, uint32_t slot, f3 
     dst[0] = make_float4(org.x, org.y, org.z, __uint_as_float(pix | (c << 27)));
     dst[1] = make_float4(dir.x, dir.y, dir.z, 0.0f);
 }
+// a reserved record no ray was written to (kHoleRecord, shadow_queue.cuh): the tracer fetches and drops it
+__device__ __forceinline__ void put_hole(const ShadowQueue& q, uint32_t slot)
+{
+    ((float4*)q.rays)[(size_t)slot * 2] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kHoleRecord));
+}
+// check_visibility's segment against the triangle it starts on; -DCRT_NO_OWN_TRI: never (A/B)
+__device__ __forceinline__ bool own_triangle_stops(f3 org, f3 dir, const TriRef& own)
+{
+#if defined(CRT_NO_OWN_TRI)
+    return false;
+#else
+    return segment_hits_triangle(org, dir, 0.0f, 0.99f, own.v(0), own.v(1), own.v(2));
+#endif
+}
 // every lane of the warp calls this: reserves rays_per_path slots for each lane that emits; returns the lane's first slot
 // and the stride between its consecutive rays (ray c of the warp's emitting paths lie next to each other)
 __device__ __forceinline__ uint32_t reserve_rays(const ShadowQueue& q, bool emits, uint32_t rays_per_path, uint32_t& stride)
@@ -208,48 +222,84 @@ __global__ void __launch_bounds__(256)
     }
     if (EX == 7) return;
     const bool shadowed = EX == 9 && opt.shadowed;
-    const uint32_t per_path = shadowed ? (uint32_t)(opt.ris_count > 0 ? opt.ris_count : 0) : 1u;
-    uint32_t stride = 0;
-    const uint32_t slot = reserve_rays(q, lit && per_path > 0, per_path, stride);
-    const uint32_t n_emit = __reduce_add_sync(0xffffffffu, lit ? per_path : 0u);
-    if ((threadIdx.x & 31) == 0 && n_emit) atomicAdd(ray_counters + 1, (unsigned long long)n_emit);
-    if (!lit) return;
-    Pcg rng = pcg_from_state(st.rng[idx]);
-    st.rng_snap[idx] = rng.state;
-    st.vmask[idx] = 0u;
-    const f3 org = surf.p + 0.001f * surf.n;  // check_visibility's segment (raytrace.hpp:45-52): direction p1 - p0, t in [0, 0.99]
     const LightsIndexed L{tris60, lights, n_lights};
-    if (EX == 8)
+    const f3 org = surf.p + 0.001f * surf.n;  // check_visibility's segment (raytrace.hpp:45-52): direction p1 - p0, t in [0, 0.99]
+    Pcg rng(0, 0);
+    if (lit)
     {
-        const float r0 = rng.next_f();
-        const float r1 = rng.next_f();
-        const float r2 = rng.next_f();
-        const LightSample ls = L.sample(r0, r1, r2);
-        put_ray(q, slot, org, ls.p - surf.p, (uint32_t)idx, 0u);
+        rng = pcg_from_state(st.rng[idx]);
+        st.rng_snap[idx] = rng.state;
+        st.vmask[idx] = 0u;
     }
-    else if (!shadowed)
+    // Own-triangle pre-test (segment_hits_triangle, bvh.cuh): a light sample below the horizon of the triangle the vertex
+    // lies on — about half of the uniformly drawn candidates — is stopped by that triangle; the ray is decided here
+    // (its visibility bit stays 0) instead of being walked through the tree.
+    uint32_t traced = 0;  // rays this lane hands to the tracer
+    if (!shadowed)
     {
-        // 09_ris.cu:66-100 with the unshadowed target function: the reservoir is final here
-        const Res r = ris_candidates(bvh, L, surf, opt.ris_count, false, rng);
-        st.sel0[idx] = make_float4(r.s.hp.x, r.s.hp.y, r.s.hp.z, r.w_sum);
-        st.sel1[idx] = make_float4(r.s.hn.x, r.s.hn.y, r.s.hn.z, __int_as_float(r.M));
-        st.sel2[idx] = make_float4(r.s.rad.x, r.s.rad.y, r.s.rad.z, 0.0f);
-        put_ray(q, slot, org, r.s.hp - surf.p, (uint32_t)idx, 0u);
+        f3 dir{0, 0, 0};
+        bool emits = false;
+        if (lit)
+        {
+            if (EX == 8)
+            {
+                const float r0 = rng.next_f();
+                const float r1 = rng.next_f();
+                const float r2 = rng.next_f();
+                const LightSample ls = L.sample(r0, r1, r2);
+                dir = ls.p - surf.p;
+            }
+            else
+            {
+                // 09_ris.cu:66-100 with the unshadowed target function: the reservoir is final here
+                const Res r = ris_candidates(bvh, L, surf, opt.ris_count, false, rng);
+                st.sel0[idx] = make_float4(r.s.hp.x, r.s.hp.y, r.s.hp.z, r.w_sum);
+                st.sel1[idx] = make_float4(r.s.hn.x, r.s.hn.y, r.s.hn.z, __int_as_float(r.M));
+                st.sel2[idx] = make_float4(r.s.rad.x, r.s.rad.y, r.s.rad.z, 0.0f);
+                dir = r.s.hp - surf.p;
+            }
+            st.rng[idx] = rng.state;
+            emits = !own_triangle_stops(org, dir, tri_at(tris60, prim));
+        }
+        uint32_t stride = 0;
+        const uint32_t slot = reserve_rays(q, emits, 1u, stride);
+        if (emits) put_ray(q, slot, org, dir, (uint32_t)idx, 0u);
+        traced = emits ? 1u : 0u;
     }
     else
     {
-        // one shadow ray per candidate; k_pt_replay draws the same candidates again once their visibilities are known
-        for (int c = 0; c < opt.ris_count; ++c)
+        // one shadow ray per candidate; k_pt_replay draws the same candidates again once their visibilities are known.
+        // The warp reserves ris_count rows of `stride` records; a lane fills its column from the top with the rays that
+        // need a walk and marks the rest of the column as holes, which the tracer skips when it fetches them.
+        const uint32_t per_path = (uint32_t)(opt.ris_count > 0 ? opt.ris_count : 0);
+        uint32_t stride = 0;
+        const uint32_t slot = reserve_rays(q, lit && per_path > 0, per_path, stride);
+        if (lit)
         {
-            const float r0 = rng.next_f();
-            const float r1 = rng.next_f();
-            const float r2 = rng.next_f();
-            (void)rng.next_f();  // the reservoir's u of this candidate
-            const LightSample ls = L.sample(r0, r1, r2);
-            put_ray(q, slot + (uint32_t)c * stride, org, ls.p - surf.p, (uint32_t)idx, (uint32_t)c);
+            const TriRef own = tri_at(tris60, prim);
+            for (int c = 0; c < opt.ris_count; ++c)
+            {
+                const float r0 = rng.next_f();
+                const float r1 = rng.next_f();
+                const float r2 = rng.next_f();
+                (void)rng.next_f();  // the reservoir's u of this candidate
+                const LightSample ls = L.sample(r0, r1, r2);
+                const f3 dir = ls.p - surf.p;
+                if (own_triangle_stops(org, dir, own)) continue;
+                put_ray(q, slot + traced * stride, org, dir, (uint32_t)idx, (uint32_t)c);
+                ++traced;
+            }
+            for (uint32_t j = traced; j < per_path; ++j) put_hole(q, slot + j * stride);
+            st.rng[idx] = rng.state;
         }
     }
-    st.rng[idx] = rng.state;
+    const uint32_t wanted = lit ? (shadowed ? (uint32_t)(opt.ris_count > 0 ? opt.ris_count : 0) : 1u) : 0u;
+    const uint32_t n_traced = __reduce_add_sync(0xffffffffu, traced), n_decided = __reduce_add_sync(0xffffffffu, wanted - traced);
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (n_traced) atomicAdd(ray_counters + 1, (unsigned long long)n_traced);
+        if (n_decided) atomicAdd(ray_counters + 2, (unsigned long long)n_decided);  // crt_rays_decided_at_emission
+    }
 }
 
 // shadowed 09_ris: Reservoir::update over the candidates with their visibilities, then the ray towards the selected sample
@@ -410,6 +460,7 @@ static int path_trace_wavefront_impl(crt_ctx* ctx, int W, int H, int frame, crt_
         const dim3 grid = tile_grid(W, rows);
         const size_t n_px = (size_t)(rows.y1 - rows.y0) * W;
         CRT_REQUIRE(n_px * (rays_per_px ? rays_per_px : 1) < 0x07ffffffull * 32ull, "too many shadow rays in one band");
+        CRT_REQUIRE((size_t)W * H < 0x07ffffffull, "image too large for the packed path | ray word");
         k_pt_begin<<<grid, 256, 0, ctx->stream>>>(W, H, rows, frame, raygen, st);
         rc = check_launch(ctx, "pt_begin");
         for (int depth = 0; rc == CRT_OK && depth < options.max_depth; ++depth)

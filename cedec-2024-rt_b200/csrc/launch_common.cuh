@@ -73,8 +73,8 @@ static int queue_prepare(crt_ctx* ctx, size_t n_pixels, ShadowQueue* q, int whic
 {
     if (!ctx->queue_counters)
     {
-        CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 6 * sizeof(unsigned)));  // count, next, two 64-bit totals
-        CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 6 * sizeof(unsigned), ctx->stream));
+        CRT_CUDA(cudaMalloc((void**)&ctx->queue_counters, 8 * sizeof(unsigned)));  // count, next, three 64-bit totals
+        CRT_CUDA(cudaMemsetAsync(ctx->queue_counters, 0, 8 * sizeof(unsigned), ctx->stream));
     }
     void*& rays = which ? ctx->queue2_rays : ctx->queue_rays;
     size_t& capacity = which ? ctx->queue2_capacity : ctx->queue_capacity;

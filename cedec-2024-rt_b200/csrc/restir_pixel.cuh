@@ -100,8 +100,23 @@ struct DeferredRay
 {
     bool want;
     f3 org, dir;
+    bool decided = false;  // the ray exists but needs no walk: the triangle it starts on stops it (visibility_ray_past_own)
 };
 CRT_HD DeferredRay visibility_ray(f3 p0, f3 n0, f3 p1) { return DeferredRay{true, p0 + 0.001f * n0, p1 - p0}; }
+// The same ray, not wanted when the triangle it starts on stops it (segment_hits_triangle, bvh.cuh): the walk would
+// report "occluded", which is what the caller has stored already.  -DCRT_NO_OWN_TRI traces every ray (A/B).
+CRT_HD DeferredRay visibility_ray_past_own(f3 p0, f3 n0, f3 p1, const TriRef& own)
+{
+    DeferredRay r = visibility_ray(p0, n0, p1);
+#if !defined(CRT_NO_OWN_TRI)
+    if (segment_hits_triangle(r.org, r.dir, 0.0f, 0.99f, own.v(0), own.v(1), own.v(2)))
+    {
+        r.want = false;
+        r.decided = true;
+    }
+#endif
+    return r;
+}
 
 // ---- 10_restir_di.cu:36-135.  With `defer` the visibility-reuse ray is returned instead of traced and the
 // reservoir is stored with visibility = false for the trace kernel to fill in.
@@ -129,7 +144,7 @@ CRT_HD DeferredRay px_generate_candidate(const Pix& px, int frame, const Bvh& bv
     r.ucw = ucw_of(r, target_function(bvh, surf.p, surf.n, r.s.hp, r.s.hn, r.s.rad, opt.shadowed));
     if (opt.reuse)
     {
-        if (defer) ray = visibility_ray(surf.p, surf.n, r.s.hp);
+        if (defer) ray = visibility_ray_past_own(surf.p, surf.n, r.s.hp, tri);  // r.s.vis is 0 = occluded here
         else r.s.vis = check_visibility(bvh, surf.p, surf.n, r.s.hp) != 0.0f ? 1u : 0u;
     }
     out.store(px.idx, r);

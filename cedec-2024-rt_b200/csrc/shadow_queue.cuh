@@ -34,10 +34,15 @@ struct ShadowQueue
     uint32_t* count;   // rays appended so far
     uint32_t* next;    // next ray to fetch (persistent kernel)
     uint32_t capacity;
-    unsigned long long* total;  // rays traced since crt_init: [0] visibility reuse, [1] resolve (crt_shadow_rays_traced)
+    unsigned long long* total;  // rays traced since crt_init: [0] visibility reuse, [1] resolve (crt_shadow_rays_traced);
+                                // [2] visibility-reuse rays settled at emission by the own-triangle pre-test
     float tmax = 0.99f;         // the segment is t in [0, tmax]: 0.99 for check_visibility (raytrace.hpp:45-52), FLT_MAX for AO rays
     uint32_t stride4 = 4;       // record size in 16-byte words: 4 = ShadowRay, 2 = compact (origin + pixel, direction) for AO rays
 };
+
+// A record whose pixel word is kHoleRecord holds no ray: a producer that reserves a fixed block of records per warp and
+// then finds some of its rays decided already (kernels_paths.cu) marks the unused ones; the tracers drop them at the fetch.
+constexpr uint32_t kHoleRecord = 0xffffffffu;
 
 #ifndef CRT_REFILL
 #define CRT_REFILL 24
@@ -50,11 +55,14 @@ constexpr uint32_t kShortQueue = 2000000u;
 
 #if defined(__CUDACC__)
 // warp-aggregated append; every lane of the warp must call it (has = whether this lane emits a ray)
-__device__ __forceinline__ void queue_push(const ShadowQueue& q, bool has, const ShadowRay& ray)
+// decided: this lane's ray was settled by the own-triangle pre-test (counted in total[2], crt_rays_decided_at_emission)
+__device__ __forceinline__ void queue_push(const ShadowQueue& q, bool has, const ShadowRay& ray, bool decided = false)
 {
     const unsigned mask = __ballot_sync(0xffffffffu, has);
-    if (mask == 0) return;
+    const unsigned dmask = __ballot_sync(0xffffffffu, decided);
     const int lane = threadIdx.x & 31;
+    if (dmask && lane == 0) atomicAdd(q.total + 2, (unsigned long long)__popc(dmask));
+    if (mask == 0) return;
     const int leader = __ffs(mask) - 1;
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(q.count, (uint32_t)__popc(mask));
@@ -225,19 +233,26 @@ __global__ void __launch_bounds__(kShadowWarps * 32, CRT_SHADOW_MINBLOCKS) k_tra
                         const float4 w0 = __ldg(src), w1 = __ldg(src + 1);
                         pix = __float_as_uint(w0.w);
                         ray_idx = my;
+                        if (pix != kHoleRecord)
+                        {
                         // visibility-reuse rays aim at freshly sampled lights: 93 % are occluded, mostly next to the light, so
                         // their walk starts at the far end (bvh.cuh: setup_ray); resolve rays aim at samples that survived
                         // the resampling — three quarters are clear, and for the rest the near end finds the blocker sooner
                         r = setup_ray(f3{w0.x, w0.y, w0.z}, f3{w1.x, w1.y, w1.z}, EPI == kEpiSoaVisibility || EPI == kEpiReservoirVisibility || EPI == kEpiBitmask);
                         walk_begin(w, r);
                         active = true;
+                        }
                     }
                 }
                 if (base + (uint32_t)__popc(idle) >= n_rays) exhausted = true;  // warp-uniform
             }
         }
         unsigned act = __ballot_sync(full, active);
-        if (act == 0) break;
+        if (act == 0)
+        {
+            if (exhausted) break;
+            continue;  // the fetch brought nothing but hole records: fetch again
+        }
 
         // ---- walk until the warp thins out
         for (;;)

@@ -191,6 +191,8 @@ def _load():
     lib.crt_shadow_rays_traced.argtypes = [P, C.POINTER(C.c_ulonglong)]
     lib.crt_inline_rays_traced.restype = C.c_int
     lib.crt_inline_rays_traced.argtypes = [P, C.POINTER(C.c_ulonglong)]
+    lib.crt_rays_decided_at_emission.restype = C.c_int
+    lib.crt_rays_decided_at_emission.argtypes = [P, C.POINTER(C.c_ulonglong)]
     lib.crt_launch_count.restype = C.c_ulonglong
     lib.crt_launch_count.argtypes = [P]
     lib.crt_raygen_lookat.restype = None
@@ -357,6 +359,13 @@ class Runtime:
         """(closest-hit, shadow / AO) rays traced inside the single-kernel examples 06-09 since crt_init"""
         out = (C.c_ulonglong * 2)()
         self._check(self.lib.crt_inline_rays_traced(self.ctx, out))
+        return int(out[0]), int(out[1])
+
+    def rays_decided_at_emission(self):
+        """(visibility-reuse rays of 10_restir_di, shadow rays of the wavefront 08_nee / 09_ris) that the emitting kernel's
+        own-triangle pre-test settled as occluded since crt_init; traced + decided = the rays the reference traces"""
+        out = (C.c_ulonglong * 2)()
+        self._check(self.lib.crt_rays_decided_at_emission(self.ctx, out))
         return int(out[0]), int(out[1])
 
     def sync(self):

@@ -322,6 +322,9 @@ class SlabRenderer:
     def shadow_rays_traced(self):
         return self.rt.shadow_rays_traced()
 
+    def rays_decided_at_emission(self):
+        return self.rt.rays_decided_at_emission()
+
     def set_math_mode(self, mode):
         self.rt.set_math_mode(mode)
 
@@ -604,6 +607,10 @@ class SlabGroup:
 
     def shadow_rays_traced(self):
         a = [s.rt.shadow_rays_traced() for s in self.slabs]
+        return sum(x[0] for x in a), sum(x[1] for x in a)
+
+    def rays_decided_at_emission(self):
+        a = [s.rt.rays_decided_at_emission() for s in self.slabs]
         return sum(x[0] for x in a), sum(x[1] for x in a)
 
     def set_math_mode(self, mode):

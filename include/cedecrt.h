@@ -133,6 +133,12 @@ int crt_shadow_rays_traced(crt_ctx* ctx, unsigned long long out[2]);
  * closest-hit rays (camera and bounce rays), out[1] shadow / AO rays, counted per path vertex as SURVEY.md section 8d
  * counts them (08_nee.cu:43,76-77; 09_ris.cu:90-93,112,116-119; 06_ao_hiprt.cu:71-82); waits for the stream */
 int crt_inline_rays_traced(crt_ctx* ctx, unsigned long long out[2]);
+/* shadow rays that needed no walk since crt_init: the per-pixel kernel that emits a ray tests it against the triangle it
+ * starts on (the reference's own intersect_ray_triangle, core.hpp:91-136, on the segment of check_visibility,
+ * raytrace.hpp:45-52); a hit there is the walk's answer "occluded".  out[0]: visibility-reuse rays of 10_restir_di
+ * (generate_candidate, 10_restir_di.cu:127-131), out[1]: shadow rays of the wavefront 08_nee / 09_ris.  These rays are
+ * not in crt_shadow_rays_traced / crt_inline_rays_traced; traced + decided = the rays the reference traces. */
+int crt_rays_decided_at_emission(crt_ctx* ctx, unsigned long long out[2]);
 /* TypedBuffer<T>(DEVICE).allocate / dtor / toDevice / toHost (common/typedbuffer.hpp:29-77);
  * memory is uninitialised, as with oroMalloc */
 int crt_malloc(crt_ctx* ctx, size_t bytes, void** out);

@@ -431,10 +431,18 @@ int main(int argc, char** argv)
             {
                 float rec[8] = {r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, (float)cls, (float)r.pix};
                 fwrite(rec, 4, 8, f);
+                const int own = vis[r.pix].index;  // the primitive the pixel's primary ray hit (the ray's origin lies on it)
+                fwrite(&own, 4, 1, f);
             }
         };
         put(vr, 1);
         put(rs, 2);
+        for (const RayRec& r : prim)  // primary rays: origin = eye, direction recomputed by the reader; only pix and prim kept
+        {
+            float rec[8] = {0, 0, 0, 0, 0, 0, 0.0f, (float)r.pix};
+            fwrite(rec, 4, 8, f);
+            fwrite(&r.occl_tri, 4, 1, f);
+        }
         fclose(f);
     }
     return 0;
