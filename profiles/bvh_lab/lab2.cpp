@@ -265,6 +265,127 @@ int main(int argc, char** argv)
         printf("== %s rays: %zu, occluded %.1f%% | walk from the root: nodes %.2f tris %.2f (occluded %.2f / %.2f, clear %.2f / %.2f)\n",
                cls == 1 ? "visibility-reuse" : "resolve", n, 100.0 * occ / n, base.nodes / n, base.tris / n, base_occ.nodes / occ,
                base_occ.tris / occ, base_clear.nodes / (n - occ), base_clear.tris / (n - occ));
+        // persistent-kernel drain: a simulation of k_trace_shadow_queue's scheduling (warps of 32 lanes fetch rays in queue order,
+        // a lane takes a new ray when fewer than 24 lanes of its warp walk; one node step per iteration) with the rays in queue
+        // order against the rays binned by segment length, longest first
+        {
+            std::vector<std::pair<float, unsigned>> q;  // (length, node steps)
+            for (size_t i = 0; i < rays.size(); i++)
+            {
+                const Ray& r = rays[i];
+                if (r.cls != cls) continue;
+                if (cls == 1)
+                {
+                    const TriRef t = tri_at(t60, r.own);
+                    float tt, u, v;
+                    if (ray_triangle(r.o, r.d, 0.0f, 0.99f, t.v(0), t.v(1), t.v(2), tt, u, v)) continue;
+                }
+                Counts c;
+                walk_any(bvh, r, far_first, 0, -1, c);
+                q.push_back({sqrtf(dot(r.d, r.d)), (unsigned)c.nodes});
+            }
+            // length statistics
+            {
+                std::vector<float> len;
+                for (auto& e : q) len.push_back(e.first);
+                std::sort(len.begin(), len.end());
+                double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+                for (auto& e : q) { const double x = log(e.first), y = e.second; sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y; }
+                const double nq = (double)q.size(), cov = sxy / nq - sx / nq * sy / nq, vx = sxx / nq - sx / nq * sx / nq, vy = syy / nq - sy / nq * sy / nq;
+                printf("   segment length: p10 %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f | correlation of log length with node steps %.2f\n", len[len.size() / 10],
+                       len[len.size() / 2], len[len.size() * 9 / 10], len[len.size() * 99 / 100], len.back(), cov / sqrt(vx * vy));
+            }
+            auto simulate = [&](const std::vector<unsigned>& steps, int warps)
+            {
+                size_t next = 0;
+                std::vector<std::vector<unsigned>> lane(warps, std::vector<unsigned>(32, 0));
+                std::vector<char> done(warps, 0);
+                unsigned long long iters = 0, busy_iters = 0, lane_steps = 0;
+                int left = warps;
+                unsigned long long span = 0;
+                while (left)
+                {
+                    ++span;
+                    for (int w = 0; w < warps; w++)
+                    {
+                        if (done[w]) continue;
+                        int active = 0;
+                        for (unsigned x : lane[w]) active += x > 0;
+                        if (active < 24 && next < steps.size())
+                            for (unsigned& x : lane[w])
+                                if (x == 0 && next < steps.size()) x = steps[next++];
+                        active = 0;
+                        for (unsigned& x : lane[w])
+                            if (x > 0) { --x; ++active; }
+                        if (active == 0 && next >= steps.size()) { done[w] = 1; --left; continue; }
+                        ++iters;
+                        lane_steps += active;
+                    }
+                }
+                (void)busy_iters;
+                printf("      %d warps: %llu warp iterations, %.1f lanes per iteration, span %llu iterations (ideal %.0f)\n", warps, iters,
+                       (double)lane_steps / iters, span, (double)lane_steps / (warps * 28.0));
+            };
+            std::vector<unsigned> in_order, binned;
+            for (auto& e : q) in_order.push_back(e.second);
+            float lo = 1e30f, hi = 0;
+            for (auto& e : q) { lo = std::min(lo, e.first); hi = std::max(hi, e.first); }
+            for (int nb : {4, 8})
+            {
+                std::vector<float> len;
+                for (auto& e : q) len.push_back(e.first);
+                std::sort(len.begin(), len.end());
+                binned.clear();
+                for (int b = nb - 1; b >= 0; b--)
+                {
+                    const float t0 = len[len.size() * b / nb], t1 = b == nb - 1 ? 1e30f : len[len.size() * (b + 1) / nb];
+                    for (auto& e : q)
+                        if (e.first >= t0 && e.first < t1) binned.push_back(e.second);
+                }
+                for (int warps : {64, 128, 256})
+                {
+                    printf("   %d length bins (quantiles), longest first:\n", nb);
+                    simulate(binned, warps);
+                    printf("   queue order:\n");
+                    simulate(in_order, warps);
+                }
+            }
+            // fixed bins: factor-2 classes of the segment length below a quarter of the scene diagonal (what the kernel can compute)
+            {
+                const float D = 470.0f;
+                for (int nb : {4, 6, 8})
+                {
+                    binned.clear();
+                    std::vector<size_t> cnt(nb, 0);
+                    auto bin_of = [&](float len) { int b = 0; float th = D / 4; while (b < nb - 1 && len < th) { ++b; th *= 0.5f; } return b; };
+                    for (int b = 0; b < nb; b++)
+                        for (auto& e : q)
+                            if (bin_of(e.first) == b) { binned.push_back(e.second); cnt[b]++; }
+                    printf("   %d fixed factor-2 bins from D/4 down, longest first (", nb);
+                    for (int b = 0; b < nb; b++) printf("%.0f%% ", 100.0 * cnt[b] / q.size());
+                    printf("):\n");
+                    for (int warps : {64, 128, 256, 512}) simulate(binned, warps);
+                }
+                for (float div : {8.0f, 16.0f, 32.0f, 64.0f})
+                {
+                    binned.clear();
+                    size_t c0 = 0;
+                    for (auto& e : q) if (e.first >= D / div) { binned.push_back(e.second); c0++; }
+                    std::vector<unsigned> tail;
+                    for (auto& e : q) if (e.first < D / div) tail.push_back(e.second);
+                    binned.insert(binned.end(), tail.rbegin(), tail.rend());  // the short rays are stored from the buffer's end downwards
+                    printf("   2 bins, long (>= D/%.0f: %.0f%%) first:\n", div, 100.0 * c0 / q.size());
+                    for (int warps : {64, 256, 512}) simulate(binned, warps);
+                }
+                printf("   queue order:\n");
+                simulate(in_order, 512);
+            }
+            // oracle: sorted by the true step count (the bound of any ordering)
+            std::vector<unsigned> sorted = in_order;
+            std::sort(sorted.rbegin(), sorted.rend());
+            printf("   sorted by true node steps (bound):\n");
+            for (int warps : {64, 128, 256}) simulate(sorted, warps);
+        }
         // the cheapest hint: the ray's own triangle (the one its origin lies on), tested by the emitting pixel kernel
         {
             size_t caught1 = 0, caught2 = 0, below = 0, below_caught = 0;
