@@ -245,6 +245,66 @@ int main(int argc, char** argv)
         printf("== primary rays: %zu | walk: nodes %.2f tris %.2f | previous hit tested first: nodes %.2f tris %.2f (+1 test) | mismatches %zu\n", n,
                a.nodes / n, a.tris / n, b.nodes / n, b.tris / n, mism);
     }
+    // config 4 (09_ris with the shadowed target function): 32 uniformly drawn light samples per path vertex, one shadow ray each.
+    // Here: the camera vertices of the recorded frame, 8 candidates each (any random numbers serve the statistics)
+    if (!prim_recs.empty() && getenv("LAB_UNIFORM"))
+    {
+        const int W = argc > 3 ? atoi(argv[3]) : 480, H = argc > 4 ? atoi(argv[4]) : 270;
+        const float eye_a[3] = {-0.579885f, 22.194597f, -6.567105f}, at_a[3] = {5.224952f, 20.847435f, 1.431192f}, up_a[3] = {0, 1, 0};
+        crt_raygen rg;
+        orc_lookat(eye_a, at_a, up_a, kPi / 4.0f, W, H, &rg);
+        std::vector<uint32_t> lights;
+        for (uint32_t i = 0; i < n_tris; i++)
+            if (has_emission(tri_at(t60, (int)i).emissive())) lights.push_back(i);
+        const LightsIndexed L{t60, lights.data(), (uint32_t)lights.size()};
+        std::vector<Ray> cand;
+        for (size_t k = 0; k < prim_recs.size(); k += 7)
+        {
+            const Ray& r = prim_recs[k];
+            if (r.own < 0 || has_emission(tri_at(t60, r.own).emissive())) continue;
+            const int row = r.pix / W, xi = r.pix % W, yi = H - 1 - row;
+            const Pix px = make_pix(xi, yi, W, H);
+            f3 ro, rd;
+            primary_ray(rg, px, W, H, ro, rd);
+            Hit h;
+            trace<false>(bvh, ro, rd, 0.0f, kFltMax, h);
+            if (h.prim < 0) continue;
+            const Surf surf = surface_from_hit(tri_at(t60, h.prim), ro, rd, h.t);
+            Pcg rng(hash_pcg4(xi, yi, 1, 7), 0);
+            for (int c = 0; c < 8; c++)
+            {
+                const float r0 = rng.next_f(), r1 = rng.next_f(), r2 = rng.next_f();
+                const LightSample ls = L.sample(r0, r1, r2);
+                Ray q;
+                q.o = surf.p + 0.001f * surf.n;
+                q.d = ls.p - surf.p;
+                q.cls = 3; q.pix = r.pix; q.own = h.prim; q.light = -1;
+                cand.push_back(q);
+            }
+        }
+        size_t n = cand.size(), occ = 0, own_hit = 0;
+        Counts far, near, bu, rest_far, rest_near;
+        size_t nrest = 0;
+        for (const Ray& r : cand)
+        {
+            Counts a, b, c;
+            const bool h = walk_any(bvh, r, true, 0, -1, a);
+            walk_any(bvh, r, false, 0, -1, b);
+            far.nodes += a.nodes; far.tris += a.tris; near.nodes += b.nodes; near.tris += b.tris;
+            occ += h;
+            const TriRef t = tri_at(t60, r.own);
+            float tt, u, v;
+            if (ray_triangle(r.o, r.d, 0.0f, 0.99f, t.v(0), t.v(1), t.v(2), tt, u, v)) { own_hit++; continue; }
+            nrest++;
+            rest_far.nodes += a.nodes; rest_far.tris += a.tris; rest_near.nodes += b.nodes; rest_near.tris += b.tris;
+            walk_bottom_up(bvh, parent, tri_node[r.own], r, false, c);
+            bu.nodes += c.nodes; bu.tris += c.tris;
+        }
+        printf("== uniform candidates from the camera vertices: %zu rays, occluded %.1f%%, own triangle stops %.1f%%\n", n, 100.0 * occ / n, 100.0 * own_hit / n);
+        printf("   all rays: far first nodes %.2f tris %.2f | near first nodes %.2f tris %.2f\n", far.nodes / n, far.tris / n, near.nodes / n, near.tris / n);
+        printf("   rays left after the own-triangle test: far first %.2f / %.2f | near first %.2f / %.2f | bottom-up from the own node %.2f / %.2f\n",
+               rest_far.nodes / nrest, rest_far.tris / nrest, rest_near.nodes / nrest, rest_near.tris / nrest, bu.nodes / nrest, bu.tris / nrest);
+    }
     for (int cls = 1; cls <= 2; cls++)
     {
         const bool far_first = cls == 1;

@@ -435,3 +435,47 @@ def test_bench_frame_hash(rt):
     print("frame_hash", h1["value"], "golden", golden.get("config5_4k"))
     if golden.get("config5_4k"):
         assert h1["value"] == golden["config5_4k"]
+
+
+# ------------------------------------------------------------------ pipelined read-back (bench.py's e2e loop)
+def test_pipelined_readback_delivers_every_frame(rt):
+    """SlabRenderer.download_pixels_async: frame i's RGBA8 image travels on a copy stream while frame i+1 renders, the
+    frames alternating between two device images.  Every delivered image must equal the one the reference's read-back
+    (copy on the frame's stream, then synchronise: 10_restir_di.cpp:386-389) delivers for the same frame, with and
+    without frame overlap."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+    import slabs
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    tris, cam, _ = bench.load_workload()
+    torch.cuda.set_device(0)
+    W, H, frames = 960, 544, 5
+    with torch.cuda.stream(torch.cuda.Stream()):
+        ref = slabs.SlabRenderer(torch, None, 0, 1, tris, cam, W, H, fused=True)
+        want = []
+        for _ in range(frames):
+            ref.frame()
+            ref.download_pixels()
+            ref.stream.synchronize()
+            want.append(ref.host_pixels.numpy().copy())
+        ref.close()
+        assert any(not np.array_equal(want[0], w) for w in want[1:])  # the accumulated image changes from frame to frame
+        for overlap in (False, True):
+            r = slabs.SlabRenderer(torch, None, 0, 1, tris, cam, W, H, fused=True, overlap=overlap)
+            got, prev = [], None
+            for _ in range(frames):
+                r.frame()
+                slot = r.download_pixels_async()
+                if prev is not None:
+                    got.append(r.wait_download(prev).numpy().copy())
+                prev = slot
+            got.append(r.wait_download(prev).numpy().copy())
+            r.join()
+            r.close()
+            for i in range(frames):
+                assert np.array_equal(got[i], want[i]), (overlap, i)
