@@ -976,7 +976,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
-    ap.add_argument("--cpu-rows", type=int, default=64, help="band height of the CPU arm's per-step sample")
+    ap.add_argument("--cpu-rows", type=int, default=192, help="band height of the CPU arm's per-step sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-line", action="store_true", help="skip the additional CRT_MATH_FAST measurement")
     ap.add_argument("--sub", type=int, default=0,
