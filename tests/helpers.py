@@ -24,6 +24,8 @@ def same(a, b):
 
 def reservoir_mismatch(a, b):
     """number of pixels whose reservoirs differ in any field (padding bytes ignored)."""
+    if len(a) == 0:
+        return 0
     bad = np.zeros(len(a), bool)
     for f in RES_FIELDS:
         x, y = a[f], b[f]
