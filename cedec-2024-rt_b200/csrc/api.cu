@@ -81,6 +81,7 @@ extern "C" int crt_shutdown(crt_ctx* ctx)
     cudaEventDestroy(ctx->ev_stop);
     if (ctx->queue_rays) cudaFree(ctx->queue_rays);
     if (ctx->queue_counters) cudaFree(ctx->queue_counters);
+    if (ctx->history_prev) cudaFree(ctx->history_prev);
     if (ctx->gbuf) cudaFree(ctx->gbuf);
     if (ctx->inline_rays) cudaFree(ctx->inline_rays);
     if (ctx->ao_count) cudaFree(ctx->ao_count);

@@ -55,6 +55,12 @@ struct crt_ctx
     // traced marks of the temporal history (restir_fast.cuh: kTracedBit) are valid for this geometry and buffer
     unsigned long long history_serial = 0;
     const void* history_buffer = nullptr;
+    // temporal reprojection in the fused frame (crt_restir_set_previous_camera): the previous frame's camera and a snapshot
+    // of its history (the merge of the fused frame is in place, a look-up at another pixel must not see this frame's records)
+    bool prev_cam_set = false;
+    crt_raygen prev_cam = {};
+    void* history_prev = nullptr;
+    size_t history_prev_pixels = 0;
     int resolve_reuse = 1;  // 0: resolve traces every shadow ray like the reference (CRT_RESOLVE_REUSE=0)
     // slab_p2p.cu: peer pointers of the neighbouring slabs and the exchange counter
     crt_slab_links links = {};

@@ -61,6 +61,20 @@ __global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
     if (t.in) d = px_candidate_temporal<Math<MODE>>(t.px, cp, frame, bvh, tris60, eye, lights, make_opt(options), temporal, g, peers, pairs);
     queue_push(q, d.want, to_shadow_ray(d, t.px.idx), d.decided);
 }
+// the same with temporal reprojection (px_candidate_temporal<..., REPROJ = true>); a kernel of its own so that the
+// in-place kernel above keeps its registers and its code
+template <class L, int MODE>
+__global__ void __launch_bounds__(256, CRT_CT_MINBLOCKS)
+    k_candidate_temporal_reprojected(int W, int H, Rows rows, int frame, Bvh bvh, const float* tris60, const crt_visibility* vis, f3 eye,
+                                     L lights, crt_options options, SoaStore temporal, GBuf g, ShadowQueue q, HaloPeers peers, Reprojection rp)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    DeferredRay d{false, {0, 0, 0}, {0, 0, 0}};
+    CandPixel cp{Vis{0.0f, 0.0f, -1}, true};
+    if (t.in) cp = classify_pixel(t.px, tris60, vis);
+    if (t.in) d = px_candidate_temporal<Math<MODE>, L, true>(t.px, cp, frame, bvh, tris60, eye, lights, make_opt(options), temporal, g, peers, 0u, rp);
+    queue_push(q, d.want, to_shadow_ray(d, t.px.idx), d.decided);
+}
 #ifndef CRT_SP_MINBLOCKS
 #define CRT_SP_MINBLOCKS 4  // 64 registers: 0.83 -> 0.75 ms per pass against 3 (profiles/r1/tuning_q.txt)
 #endif
@@ -91,8 +105,24 @@ __global__ void __launch_bounds__(256)
 void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
                                const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
                                const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
-                               ShadowQueue q, HaloPeers peers)
+                               ShadowQueue q, HaloPeers peers, const Reprojection* rp)
 {
+    if (rp)
+    {
+        if (table)
+        {
+            const LightsTable L{table, n_lights};
+            auto k = exact ? k_candidate_temporal_reprojected<LightsTable, 1> : k_candidate_temporal_reprojected<LightsTable, 0>;
+            k<<<grid, 256, 0, st>>>(W, H, rows, frame, bvh, tris60, vis, eye, L, options, T, g, q, peers, *rp);
+        }
+        else
+        {
+            const LightsIndexed L{tris60, light_ids, n_lights};
+            auto k = exact ? k_candidate_temporal_reprojected<LightsIndexed, 1> : k_candidate_temporal_reprojected<LightsIndexed, 0>;
+            k<<<grid, 256, 0, st>>>(W, H, rows, frame, bvh, tris60, vis, eye, L, options, T, g, q, peers, *rp);
+        }
+        return;
+    }
     if (table)
     {
         const LightsTable L{table, n_lights};
@@ -138,7 +168,7 @@ int preload();
 void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
                                const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
                                const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
-                               ShadowQueue q, HaloPeers peers);
+                               ShadowQueue q, HaloPeers peers, const Reprojection* rp);
 void launch_spatial(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye,
                     crt_options options, SoaStore in, SoaStore out, GBuf g, HaloPeers peers);
 void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H, Rows rows, const float* tris60,
@@ -150,7 +180,7 @@ int preload();
 void launch_candidate_temporal(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, Bvh bvh,
                                const float* tris60, const crt_visibility* vis, f3 eye, const LightRec* table,
                                const uint32_t* light_ids, uint32_t n_lights, crt_options options, SoaStore T, GBuf g,
-                               ShadowQueue q, HaloPeers peers);
+                               ShadowQueue q, HaloPeers peers, const Reprojection* rp);
 void launch_spatial(cudaStream_t st, bool exact, dim3 grid, int W, int H, Rows rows, int frame, int pass, Bvh bvh, f3 eye,
                     crt_options options, SoaStore in, SoaStore out, GBuf g, HaloPeers peers);
 void launch_resolve(cudaStream_t st, dim3 grid, crt_float4* accum, int W, int H, Rows rows, const float* tris60,
@@ -284,6 +314,14 @@ extern "C" int crt_restir_output_buffer(crt_options options, const crt_restir_bu
 
 extern "C" int crt_restir_is_fused(crt_options options) { return fused(options) ? 1 : 0; }
 
+extern "C" int crt_restir_set_previous_camera(crt_ctx* ctx, const crt_raygen* previous_raygen)
+{
+    CRT_REQUIRE(ctx, "null context");
+    ctx->prev_cam_set = previous_raygen != nullptr;
+    if (previous_raygen) ctx->prev_cam = *previous_raygen;
+    return CRT_OK;
+}
+
 extern "C" int crt_restir_class_plane(crt_ctx* ctx, void** out)
 {
     CRT_REQUIRE(ctx && out, "null argument");
@@ -311,10 +349,19 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
         CRT_REQUIRE(!options.use_spatial_resampling || options.spatial_resampling_passes != 1,
                     "slab links need 0 or >= 2 spatial passes (one signal/wait per pass orders the neighbours)");
     }
+    if (ctx->prev_cam_set)
+    {
+        // a look-up at another pixel reads rows this context may not compute or hold
+        CRT_REQUIRE(!ctx->links_set && ctx->row_begin <= 0 && (ctx->row_end < 0 || ctx->row_end >= H),
+                    "temporal reprojection in the fused frame needs the whole image on one context");
+    }
     if (!fused(options))
     {
         rc = crt_generate_candidate(ctx, W, H, frame, geom, triangles, b->visibility, eye, lights, options, b->reservoir0);
-        if (rc == CRT_OK) rc = crt_temporal_resampling(ctx, W, H, frame, geom, triangles, b->visibility, eye, options, b->temporal, b->reservoir0);
+        if (rc == CRT_OK)
+            rc = ctx->prev_cam_set ? crt_temporal_resampling_reprojected(ctx, W, H, frame, geom, triangles, b->visibility, eye, options,
+                                                                         ctx->prev_cam, b->temporal, b->reservoir0)
+                                   : crt_temporal_resampling(ctx, W, H, frame, geom, triangles, b->visibility, eye, options, b->temporal, b->reservoir0);
         if (rc == CRT_OK) rc = crt_save_temporal_reservoir(ctx, W, H, b->reservoir0, b->temporal);
         return rc;
     }
@@ -354,9 +401,28 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
         rc = light_table_for(ctx, geom, tris60, (const uint32_t*)lights.data, n_lights, &table);
         if (rc != CRT_OK) return rc;
     }
+    Reprojection rp;
+    const bool reproject = ctx->prev_cam_set && options.use_temporal_resampling;
+    if (reproject)
+    {
+        // snapshot of last frame's history: this frame's records overwrite `temporal` while other pixels still look theirs up
+        if (ctx->history_prev_pixels < n)
+        {
+            if (ctx->history_prev) CRT_CUDA(cudaFree(ctx->history_prev));
+            ctx->history_prev = nullptr;
+            ctx->history_prev_pixels = 0;
+            CRT_CUDA(cudaMalloc(&ctx->history_prev, n * 72));
+            ctx->history_prev_pixels = n;
+        }
+        CRT_CUDA(cudaMemcpyAsync(ctx->history_prev, b->temporal.data, n * 72, cudaMemcpyDeviceToDevice, ctx->stream));
+        rp.history = SoaStore{(char*)ctx->history_prev, n};
+        rp.prev_cam = ctx->prev_cam;
+        rp.W = W;
+        rp.H = H;
+    }
     CRT_MODE_NS(ctx, launch_candidate_temporal)(
         ctx->stream, exact, grid, W, H, rows, frame, geom->view(), tris60, vis, to_f3(eye), table,
-        (const uint32_t*)lights.data, n_lights, options, T, g, q, peers);
+        (const uint32_t*)lights.data, n_lights, options, T, g, q, peers, reproject ? &rp : nullptr);
     rc = check_launch(ctx, "candidate_temporal");
     if (rc != CRT_OK || !options.use_visibility_reuse) return rc;
     ShadowSink sink{nullptr, nullptr, 0, (uint32_t*)T.plane(0, 0)};

@@ -228,10 +228,20 @@ CRT_HD CandPixel classify_pixel(const Pix& px, const float* tris60, const crt_vi
 // lanes of `lanes` whose pair partner (lane ^ 1) is in `lanes` too
 CRT_HD unsigned complete_pairs(unsigned lanes) { return lanes & (((lanes & 0x55555555u) << 1) | ((lanes & 0xaaaaaaaau) >> 1)); }
 
-template <class M, class L>
+// REPROJ (extension): the history is read from `history` — a snapshot of last frame's `temporal` —
+// at the pixel this surface point had in the previous frame's camera (reproject_pixel, restir_core.cuh), Reservoir{} when
+// it had none; `temporal` is only written.  Otherwise the history is `temporal` at this pixel, merged in place.
+struct Reprojection
+{
+    SoaStore history{nullptr, 0};
+    crt_raygen prev_cam{};
+    int W = 0, H = 0;
+};
+template <class M, class L, bool REPROJ = false>
 CRT_HD DeferredRay px_candidate_temporal(const Pix& px, const CandPixel& cp, int frame, const Bvh& bvh, const float* tris60,
                                          f3 eye, const L& lights, const Opt& opt_in, const SoaStore& temporal,
-                                         const GBuf& g, const HaloPeers& peers = HaloPeers(), unsigned pair_mask = 0u)
+                                         const GBuf& g, const HaloPeers& peers = HaloPeers(), unsigned pair_mask = 0u,
+                                         const Reprojection& rp = Reprojection())
 {
     Opt opt = opt_in;
     opt.shadowed = false;  // compile-time constant here: no traversal code inside the target function
@@ -257,7 +267,15 @@ CRT_HD DeferredRay px_candidate_temporal(const Pix& px, const CandPixel& cp, int
     if (opt.temporal)
     {
         Pcg rng_t(hash_pcg4(px.xi, px.yi, frame, 1), 0);
-        candidate_survives = !temporal_merge<M>(bvh, surf, eye, opt, temporal.load(px.idx), r, rng_t);
+        Res history;
+        if (REPROJ)
+        {
+            int xp, yp;
+            history = reproject_pixel(to_raygen(rp.prev_cam), rp.W, rp.H, surf.p, xp, yp) ? rp.history.load(xp + (rp.H - yp - 1) * rp.W)
+                                                                                          : empty_res();
+        }
+        else history = temporal.load(px.idx);
+        candidate_survives = !temporal_merge<M>(bvh, surf, eye, opt, history, r, rng_t);
     }
     if (opt.reuse && candidate_survives)
     {

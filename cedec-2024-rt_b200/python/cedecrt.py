@@ -163,6 +163,7 @@ def _load():
         "crt_restir_frame_end": [P, I, I, G, B, Float3, Options, C.POINTER(RestirBuffers)],
         "crt_restir_output_buffer": [Options, C.POINTER(RestirBuffers), C.POINTER(B)],
         "crt_restir_is_fused": [Options],
+        "crt_restir_set_previous_camera": [P, C.POINTER(RayGenerator)],
         "crt_restir_class_plane": [P, C.POINTER(C.c_void_p)],
         "crt_reservoir_export_aos": [P, I, I, B, B],
         "crt_reservoir_import_aos": [P, I, I, B, B],
@@ -484,6 +485,10 @@ class Runtime:
         return RestirBuffers(pixels.arg(), accumulation.arg(), visibility.arg(), reservoir0.arg(), reservoir1.arg(),
                              temporal.arg())
 
+    def restir_set_previous_camera(self, raygen):
+        """temporal reprojection inside the fused frame: the previous frame's camera, or None for the reference's same-pixel history"""
+        self._check(self.lib.crt_restir_set_previous_camera(self.ctx, C.byref(raygen) if raygen is not None else None))
+
     def restir_di_frame(self, W, H, frame, geom, triangles, raygen, eye, lights, options, bufs):
         self._check(self.lib.crt_restir_di_frame(self.ctx, W, H, frame, geom.handle, triangles.arg(), raygen,
                                                  Float3(*eye), lights.arg(), options, C.byref(bufs)))
@@ -571,11 +576,9 @@ class RestirDI:
     def __init__(self, rt, width, height, triangles_host, eye, lookat_pt, options=None, fused=False, reproject=False):
         """fused=False: the reference's launch list, one crt_* call per kernel, AoS reservoir buffers (drop-in mode);
         fused=True: one crt_restir_di_frame call per frame (SoA reservoirs inside the same buffers).
-        reproject=True (extension, launch-list mode only): temporal resampling looks the previous reservoir up at the pixel
-        the surface point had in the previous frame's camera (crt_temporal_resampling_reprojected); set_camera() moves the
-        camera and clears the accumulation like the reference's loop (10_restir_di.cpp:257-267)."""
-        if fused and reproject:
-            raise CrtError("temporal reprojection runs on the per-kernel path: the fused frame merges the history in place")
+        reproject=True (extension): temporal resampling looks the previous reservoir up at the pixel the surface point had
+        in the previous frame's camera (crt_temporal_resampling_reprojected; in fused mode crt_restir_set_previous_camera);
+        set_camera() moves the camera and clears the accumulation like the reference's loop (10_restir_di.cpp:257-267)."""
         self.rt, self.W, self.H, self.fused = rt, width, height, fused
         self.reproject, self.prev_raygen = reproject, None
         self.prefetch = False  # fused + crt_set_frame_overlap: trace the next frame's primary rays right after issuing a frame
@@ -625,7 +628,12 @@ class RestirDI:
         f = self.frame_index
         if self.fused:
             bufs = rt.restir_buffers(self.pixels, self.accumulation, v, self.reservoir0, self.reservoir1, self.temporal)
+            if self.reproject:
+                rt.restir_set_previous_camera(self.prev_raygen)  # None before the first frame: no history to look up
             rt.restir_di_frame(W, H, f, g, t, self.raygen, eye, self.lights, o, bufs)
+            if self.reproject:
+                self.prev_raygen = RayGenerator.from_buffer_copy(bytes(self.raygen))
+                rt.restir_set_previous_camera(None)  # the context serves other hosts too: leave it as the reference behaves
             if self.prefetch:
                 rt.restir_prefetch_raycast(W, H, g, self.raygen)
             return

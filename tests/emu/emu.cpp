@@ -374,10 +374,24 @@ extern "C"
     // ---- the fused frame (csrc/kernels_fast.cu: crt_restir_di_frame), same kernel sequence, rays traced inline.
     // temporal / res_a / res_b: sector-planar storage of W*H*76 bytes each (restir_fast.cuh: SoaStore).
     // Final spatial output: res_a for an odd number of passes, res_b for an even one, `temporal` if spatial is off.
+    // prev_rg != nullptr: temporal reprojection inside the fused frame (crt_restir_set_previous_camera): the history is a
+    // snapshot of `temporal`, read at the reprojected pixel
+    void emu_restir_frame_fast_reprojected(int W, int H, int frame, void* gp, const crt_triangle* tris, const crt_raygen* rg,
+                                           const float* eye_p, const uint32_t* lights, int nlights, const crt_options* options,
+                                           crt_visibility* vis, char* temporal, char* res_a, char* res_b, crt_float4* accum,
+                                           uint32_t* pixels, const crt_raygen* prev_rg);
     void emu_restir_frame_fast(int W, int H, int frame, void* gp, const crt_triangle* tris, const crt_raygen* rg,
                                const float* eye_p, const uint32_t* lights, int nlights, const crt_options* options,
                                crt_visibility* vis, char* temporal, char* res_a, char* res_b, crt_float4* accum,
                                uint32_t* pixels)
+    {
+        emu_restir_frame_fast_reprojected(W, H, frame, gp, tris, rg, eye_p, lights, nlights, options, vis, temporal, res_a, res_b,
+                                          accum, pixels, nullptr);
+    }
+    void emu_restir_frame_fast_reprojected(int W, int H, int frame, void* gp, const crt_triangle* tris, const crt_raygen* rg,
+                                           const float* eye_p, const uint32_t* lights, int nlights, const crt_options* options,
+                                           crt_visibility* vis, char* temporal, char* res_a, char* res_b, crt_float4* accum,
+                                           uint32_t* pixels, const crt_raygen* prev_rg)
     {
         const Bvh bvh = ((EmuGeom*)gp)->view();
         const float* t60 = (const float*)tris;
@@ -390,11 +404,27 @@ extern "C"
         const SoaStore T{temporal, n}, A{res_a, n}, B{res_b, n};
         const LightsIndexed L{t60, lights, (uint32_t)nlights};
         launch(W, H, [&](Pix p) { px_raycast(p, W, H, bvh, *rg, vis); });
+        std::vector<char> snapshot;
+        Reprojection rp;
+        if (prev_rg && opt.temporal)
+        {
+            snapshot.assign(temporal, temporal + n * 72);
+            rp.history = SoaStore{snapshot.data(), n};
+            rp.prev_cam = *prev_rg;
+            rp.W = W;
+            rp.H = H;
+        }
+        const bool reproject = prev_rg && opt.temporal;
         launch(W, H, [&](Pix p)
                {
                    const CandPixel cp = classify_pixel(p, t60, vis);
-                   const DeferredRay d = g_math_mode ? px_candidate_temporal<Math<1>>(p, cp, frame, bvh, t60, eye, L, opt, T, g)
-                                                     : px_candidate_temporal<Math<0>>(p, cp, frame, bvh, t60, eye, L, opt, T, g);
+                   DeferredRay d;
+                   if (reproject)
+                       d = g_math_mode ? px_candidate_temporal<Math<1>, LightsIndexed, true>(p, cp, frame, bvh, t60, eye, L, opt, T, g, HaloPeers(), 0u, rp)
+                                       : px_candidate_temporal<Math<0>, LightsIndexed, true>(p, cp, frame, bvh, t60, eye, L, opt, T, g, HaloPeers(), 0u, rp);
+                   else
+                       d = g_math_mode ? px_candidate_temporal<Math<1>>(p, cp, frame, bvh, t60, eye, L, opt, T, g)
+                                       : px_candidate_temporal<Math<0>>(p, cp, frame, bvh, t60, eye, L, opt, T, g);
                    if (d.want)
                    {
                        Hit h;

@@ -207,14 +207,23 @@ class EmuFusedFrame:
         self.accum = np.zeros((n, 4), np.float32)
         self.pixels = np.zeros(n, np.uint32)
         self.frame = 0
+        self.emu, self.reproject, self.prev_rg = emu, False, None
+
+    def set_camera(self, eye, center):
+        """the reference's loop on a camera move: new ray generator, accumulation cleared (10_restir_di.cpp:257-267)"""
+        self.eye = np.asarray(eye, np.float32)
+        self.rg = self.emu.lookat(eye, center, self.W, self.H)
+        self.accum[:] = 0
 
     def step(self):
         self.frame += 1
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         lights = self.lights if len(self.lights) else np.zeros(1, np.uint32)
-        self.L.emu_restir_frame_fast(self.W, self.H, self.frame, self.g, p(self.tris), p(self.rg), p(self.eye),
-                                     p(lights), len(self.lights), p(self.opt), p(self.vis), p(self.T), p(self.A),
-                                     p(self.B), p(self.accum), p(self.pixels))
+        prev = p(self.prev_rg) if self.reproject and self.prev_rg is not None else None
+        self.L.emu_restir_frame_fast_reprojected(self.W, self.H, self.frame, self.g, p(self.tris), p(self.rg), p(self.eye),
+                                                 p(lights), len(self.lights), p(self.opt), p(self.vis), p(self.T), p(self.A),
+                                                 p(self.B), p(self.accum), p(self.pixels), prev)
+        self.prev_rg = self.rg.copy()
 
     def aos(self, soa):
         out = np.zeros(self.W * self.H, orc.RESERVOIR)

@@ -363,8 +363,37 @@ def test_temporal_reprojection_bit_exact_with_a_moving_camera(rt, exact, port):
     assert same(one.to_host(), two.to_host())
     with pytest.raises(cedecrt.CrtError, match="in place"):
         rt.temporal_resampling_reprojected(w, h, 4, app.geom, app.triangles, app.visibility, app.eye, app.options, prev_rg, one, one)
-    with pytest.raises(cedecrt.CrtError, match="per-kernel path"):
-        cedecrt.RestirDI(rt, w, h, tris, *CAM_AO, cedecrt.Options(**KW), fused=True, reproject=True)
+    # the fused frame with the same look-up (crt_restir_set_previous_camera): the same frames, bit for bit — and with options
+    # that take the per-kernel path inside crt_restir_di_frame (the shadowed target function) against the launch list
+    fused = cedecrt.RestirDI(rt, w, h, tris, *CAM_AO, cedecrt.Options(**KW), fused=True, reproject=True)
+    for _ in range(2):
+        fused.frame()
+    fused.set_camera((8.4, 7.8, 8.1), (0.1, 0.0, -0.1))
+    fused.frame()
+    fused.set_camera((8.9, 7.5, 8.3), (0.2, 0.1, -0.2))
+    fused.frame()
+    assert same(fused.accumulation.to_host().view(np.float32).reshape(-1, 4), a.accum)
+    d = a.vis["index"] >= 0
+    d[d] = ~(tris["emissive"] > 0).any(1)[a.vis["index"][d]]
+    assert reservoir_mismatch(fused.export_aos(fused.temporal)[d], a.temporal[d]) == 0
+    assert reservoir_mismatch(fused.output_reservoirs()[d], a.out[d]) == 0
+    assert same(fused.pixels.to_host(), app.pixels.to_host())
+    kw_sh = dict(KW, use_shadowed_target_function=1, ris_sample_count=4)
+    x = cedecrt.RestirDI(rt, w, h, tris, *CAM_AO, cedecrt.Options(**kw_sh), fused=True, reproject=True)
+    y = cedecrt.RestirDI(rt, w, h, tris, *CAM_AO, cedecrt.Options(**kw_sh), fused=False, reproject=True)
+    for app2 in (x, y):
+        app2.frame()
+        app2.set_camera((8.4, 7.8, 8.1), (0.1, 0.0, -0.1))
+        app2.frame()
+    assert same(x.accumulation.to_host(), y.accumulation.to_host()) and same(x.temporal.to_host(), y.temporal.to_host())
+    # one context must hold the whole image
+    rt.set_row_range(8, 40)
+    try:
+        with pytest.raises(cedecrt.CrtError, match="whole image"):
+            fused.frame()
+    finally:
+        rt.set_row_range(0, -1)
+        rt.restir_set_previous_camera(None)
 
 
 # ------------------------------------------------------------------ frame overlap

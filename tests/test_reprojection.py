@@ -9,7 +9,7 @@ import pytest
 
 import orc
 from helpers import reservoir_mismatch, same, small_scene
-from test_emu_parity import emu, lit_blocks_ao  # noqa: F401  (fixture)
+from test_emu_parity import EmuFusedFrame, emu, lit_blocks_ao  # noqa: F401  (fixture)
 
 CAM_CB = ((0.0, 2.7, 9.0), (0.0, 2.7, 0.0))
 CAM_AO = ((8.0, 8.0, 8.0), (0.0, 0.0, 0.0))
@@ -90,3 +90,39 @@ def test_device_code_equals_the_specification_with_a_moving_camera(emu, port, mo
     d[d] = ~em[a.vis["index"][d]]
     assert (a.temporal["M"][d] > 32).mean() > 0.8
     assert reservoir_mismatch(a.temporal[d], c.temporal[d]) > 0.3 * d.sum()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_frame_with_reprojection_equals_the_specification(emu, port, mode):
+    """crt_restir_set_previous_camera: the fused frame's candidate + temporal body with the history looked up at the
+    reprojected pixel in a snapshot of last frame's records (the merge itself stays in place) — device code on the host —
+    against the specification's kernel chain, camera moving twice; and with an unmoved camera against the plain fused frame"""
+    tris = lit_blocks_ao()
+    W, H = 128, 72
+    spec = moved_camera_chain(port, tris, W, H, mode, True)
+    emu.set_math_mode(mode)
+    g = emu.geom_build(tris)
+    f = EmuFusedFrame(emu, W, H, tris, g, *CAM_AO, orc.make_options(**KW))
+    f.reproject = True
+    for _ in range(2):
+        f.step()
+    f.set_camera((8.4, 7.8, 8.1), (0.1, 0.0, -0.1))
+    f.step()
+    f.set_camera((8.9, 7.5, 8.3), (0.2, 0.1, -0.2))
+    f.step()
+    assert same(f.vis["index"], spec.vis["index"])
+    d = spec.vis["index"] >= 0
+    em = (tris["emissive"] > 0).any(1)
+    d[d] = ~em[spec.vis["index"][d]]
+    assert reservoir_mismatch(spec.temporal[d], f.aos(f.T)[d]) == 0 and reservoir_mismatch(spec.out[d], f.output()[d]) == 0
+    assert same(f.accum, spec.accum)
+    # unmoved camera: reprojection on and off give the same frames
+    a = EmuFusedFrame(emu, W, H, tris, g, *CAM_AO, orc.make_options(**KW))
+    b = EmuFusedFrame(emu, W, H, tris, g, *CAM_AO, orc.make_options(**KW))
+    b.reproject = True
+    for _ in range(3):
+        a.step()
+        b.step()
+    assert same(a.T, b.T) and same(a.accum, b.accum) and same(a.pixels, b.pixels)
+    emu.set_math_mode(0)
+    emu.geom_free(g)
