@@ -142,7 +142,15 @@ CRT_HD u8w load_u8w(const void* p)
 {
 #if defined(__CUDA_ARCH__)
     u8w v;
+    // L1::no_allocate: these records are gathered once per use — 32 uniformly random light records per pixel out of 56 MB,
+    // a neighbour's reservoir head — and never found in the L1 again (hit rate 6 % in k_candidate_temporal); kept out of it
+    // they stop evicting what is reused.  Measured at 4K (profiles/r2/tuning.txt, batch 24): k_candidate_temporal 2.265 ->
+    // 2.149 ms, k_spatial_fast 0.745 -> 0.721 ms per pass; an L2::128B fetch hint on the same loads changed nothing.
+#if defined(CRT_U8W_ALLOC)
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+    asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=r"(v.lo.x), "=r"(v.lo.y), "=r"(v.lo.z), "=r"(v.lo.w), "=r"(v.hi.x), "=r"(v.hi.y), "=r"(v.hi.z), "=r"(v.hi.w)
         : "l"(p));
     return v;
