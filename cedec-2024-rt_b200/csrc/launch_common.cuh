@@ -53,7 +53,7 @@ __device__ __forceinline__ ShadowRay to_shadow_ray(const DeferredRay& d, int pix
 static __global__ void __launch_bounds__(256) k_build_light_table(uint32_t n, const float* tris60, const uint32_t* lights, LightRec* table)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) table[i] = make_light_rec(tris60, lights[i]);
+    if (i < n) table[i] = make_light_rec(tris60, lights[i], n);
 }
 }  // namespace crt
 

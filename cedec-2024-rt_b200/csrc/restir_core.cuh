@@ -109,6 +109,7 @@ struct LightSample
 {
     f3 p, n, emissive;
     float area;
+    float pdf;  // LightsTable only: 1.0f / size * 1.0f / area (10_restir_di.cu:98-99), divided once when the table is built
 };
 // core.hpp:261-285 plus what the callers read from the same triangle (emissive, area_of).
 // Two interchangeable sources with identical results:
@@ -120,6 +121,7 @@ struct LightsIndexed
     const float* tris60;
     const uint32_t* lights;
     uint32_t n;
+    static constexpr bool kHasPdf = false;
     struct Raw
     {
         const float* tri;
@@ -141,6 +143,7 @@ struct LightsIndexed
         const float len = length(c);
         ls.n = c / len;        // normal_of
         ls.area = 0.5f * len;  // area_of
+        ls.pdf = 0.0f;
         ls.emissive = t.emissive();
         return ls;
     }
@@ -148,24 +151,26 @@ struct LightsIndexed
 };
 struct alignas(16) LightRec  // 64 bytes
 {
-    float v0x, v0y, v0z, area;
+    float v0x, v0y, v0z, pdf;  // pdf = 1.0f / size * 1.0f / area: what every candidate divides by (saves one of its seven IEEE divisions)
     float v1x, v1y, v1z, nx;
     float v2x, v2y, v2z, ny;
     float ex, ey, ez, nz;
 };
-CRT_HD LightRec make_light_rec(const float* tris60, uint32_t tri_index)
+CRT_HD LightRec make_light_rec(const float* tris60, uint32_t tri_index, uint32_t n_lights)
 {
     const TriRef t = tri_at(tris60, (int)tri_index);
     const f3 v0 = t.v(0), v1 = t.v(1), v2 = t.v(2), e = t.emissive();
     const f3 c = cross(v1 - v0, v2 - v0);
     const float len = length(c);
     const f3 n = c / len;
-    return LightRec{v0.x, v0.y, v0.z, 0.5f * len, v1.x, v1.y, v1.z, n.x, v2.x, v2.y, v2.z, n.y, e.x, e.y, e.z, n.z};
+    const float inv_n = 1.0f / (float)n_lights;  // as ris_candidates computes it
+    return LightRec{v0.x, v0.y, v0.z, inv_n * 1.0f / (0.5f * len), v1.x, v1.y, v1.z, n.x, v2.x, v2.y, v2.z, n.y, e.x, e.y, e.z, n.z};
 }
 struct LightsTable
 {
     const LightRec* table;
     uint32_t n;
+    static constexpr bool kHasPdf = true;
     struct Raw
     {
         u4 a, b, c, d;
@@ -226,7 +231,8 @@ struct LightsTable
         LightSample ls;
         ls.p = bary_point(v0, v1, v2, b.x, b.y);
         ls.n = f3{u2f(b4.w), u2f(c4.w), u2f(d.w)};
-        ls.area = u2f(a.w);
+        ls.area = 0.0f;  // folded into pdf
+        ls.pdf = u2f(a.w);
         ls.emissive = f3{u2f(d.x), u2f(d.y), u2f(d.z)};
         return ls;
     }
@@ -285,7 +291,13 @@ CRT_HD f2 sample_2d_gaussian(float rv0, float rv1)  // reservoir.hpp:89-95
     const float a = -2.0f * M::log(rv0);
     const float radius = sqrtf(a > 0.0f ? a : 0.0f);
     const float phi = 2.0f * kPi * rv1;
+#if defined(__CUDA_ARCH__) && !defined(CRT_NO_SINCOS)
+    float s, c;
+    M::sincos(phi, s, c);
+    return {radius * c, radius * s};
+#else
     return {radius * M::cos(phi), radius * M::sin(phi)};
+#endif
 }
 CRT_HD float ucw_of(const Res& r, float p_hat) { return p_hat > 0.0f ? r.w_sum / ((float)r.M * p_hat) : 0.0f; }
 
@@ -315,9 +327,8 @@ CRT_HD Opt make_opt(const crt_options& o)
 // RIS over the emissive triangles: generate_candidate (10_restir_di.cu:78-111) and 09_ris.cu:66-100.
 // Randoms are drawn left to right: light pick, two barycentric randoms, then the reservoir's u.
 // One candidate: Reservoir::update (reservoir.hpp:22-29) with weight p_hat / light_pdf
-CRT_HD void ris_apply(const Surf& surf, const LightSample& ls, float inv_n, float u, float p_hat, Res& r)
+CRT_HD void ris_apply_pdf(const Surf& surf, const LightSample& ls, float light_pdf, float u, float p_hat, Res& r)
 {
-    const float light_pdf = inv_n * 1.0f / ls.area;  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
     const float weight = p_hat / light_pdf;
     r.w_sum += weight;
     r.M += 1;
@@ -331,9 +342,16 @@ CRT_HD void ris_apply(const Surf& surf, const LightSample& ls, float inv_n, floa
         r.s.vis = 0;
     }
 }
+CRT_HD void ris_apply(const Surf& surf, const LightSample& ls, float inv_n, float u, float p_hat, Res& r)
+{
+    ris_apply_pdf(surf, ls, inv_n * 1.0f / ls.area, u, p_hat, r);  // 1.0f / size * 1.0f / area (10_restir_di.cu:98-99)
+}
+template <class L>
 CRT_HD void ris_update(const Bvh& bvh, const Surf& surf, const LightSample& ls, float inv_n, float u, bool shadowed, Res& r)
 {
-    ris_apply(surf, ls, inv_n, u, target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed), r);
+    const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
+    if (L::kHasPdf) ris_apply_pdf(surf, ls, ls.pdf, u, p_hat, r);
+    else ris_apply(surf, ls, inv_n, u, p_hat, r);
 }
 // The four randoms of a candidate do not depend on earlier candidates, so the light records of kRisBatch
 // candidates are requested before the first one is used: kRisBatch gathers in flight per thread instead of one
@@ -422,7 +440,7 @@ CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int
             raw[b] = lights.fetch(r0, pair_mask);
         }
 #pragma unroll
-        for (int b = 0; b < kRisBatch; ++b) ris_update(bvh, surf, lights.finish(raw[b], r1[b], r2[b]), inv_n, u[b], shadowed, r);
+        for (int b = 0; b < kRisBatch; ++b) ris_update<L>(bvh, surf, lights.finish(raw[b], r1[b], r2[b]), inv_n, u[b], shadowed, r);
     }
     for (; i < count; ++i)
     {
@@ -430,7 +448,7 @@ CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int
         const float r1 = rng.next_f();
         const float r2 = rng.next_f();
         const float u = rng.next_f();
-        ris_update(bvh, surf, lights.finish(lights.fetch(r0, pair_mask), r1, r2), inv_n, u, shadowed, r);
+        ris_update<L>(bvh, surf, lights.finish(lights.fetch(r0, pair_mask), r1, r2), inv_n, u, shadowed, r);
     }
     return r;
 }
