@@ -639,7 +639,7 @@ def run_cuda(args):
             if "value" in out["ref_gpu"]:
                 out["ref_gpu"]["vs_ours"] = round(out["value"] / out["ref_gpu"]["value"], 3)
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_sample(r, tris, cam, W, H)
+            out["cpu_baseline"] = cpu_baseline_sample(r, tris, cam, W, H, rows=args.cpu_rows)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
