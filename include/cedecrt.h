@@ -209,9 +209,12 @@ int crt_temporal_resampling(crt_ctx* ctx, int width, int height, int frame, crt_
  * (RayGenerator::shoot inverted, nearest sample point; no history behind that camera or outside its image); everything
  * else — M cap, rejection heuristics, merge, random stream — is the reference kernel's.  With an unmoved camera the
  * result equals crt_temporal_resampling bit for bit.  Specification: oracle/port/oracle_port.cpp: reproject_pixel.
- * Per-kernel path only: the fused frame merges in place, which a lookup at another pixel forbids; with row slabs the
+ * This is the launch-list form (`previous_reservoirs` and `reservoirs` must be different buffers); with row slabs the
  * rows of `previous_reservoirs` a slab reads are no longer bounded by the spatial halo (the host must provide all rows
  * the camera motion can reach).  crt_launch name: "temporal_resampling_reprojected" (previous_raygen is the 9th param). */
+int crt_temporal_resampling_reprojected(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
+                                        crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
+                                        crt_raygen previous_raygen, crt_buffer previous_reservoirs, crt_buffer reservoirs);
 /* The same look-up inside the fused frame (crt_restir_frame_begin / crt_restir_di_frame): with a previous camera set,
  * the frame's candidate + temporal kernel reads the history at the reprojected pixel — from a snapshot of `temporal`
  * the library takes at the start of the frame (72 bytes per pixel of its own; the fused merge writes `temporal` in
@@ -219,9 +222,6 @@ int crt_temporal_resampling(crt_ctx* ctx, int width, int height, int frame, crt_
  * reference's behaviour, the default).  One context must hold the whole image (no row range, no slab links).  With the
  * previous camera equal to the current one the frame equals the plain fused frame bit for bit. */
 int crt_restir_set_previous_camera(crt_ctx* ctx, const crt_raygen* previous_raygen);
-int crt_temporal_resampling_reprojected(crt_ctx* ctx, int width, int height, int frame, crt_geometry geom, crt_buffer triangles,
-                                        crt_buffer visibility_buffer, crt_float3 eye, crt_options options,
-                                        crt_raygen previous_raygen, crt_buffer previous_reservoirs, crt_buffer reservoirs);
 /* 10_restir_di.cu:239-254 — note the reference's parameter names are swapped: the first buffer is the source */
 int crt_save_temporal_reservoir(crt_ctx* ctx, int width, int height, crt_buffer src, crt_buffer dst);
 /* 10_restir_di.cu:256-388 */
