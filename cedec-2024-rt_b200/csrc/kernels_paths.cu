@@ -104,19 +104,29 @@ __global__ void __launch_bounds__(256)
         rdp = st.rd_prim[idx];
         live = __float_as_int(rdp.w) != kPathDead;
     }
+    // one reservation per block (two same-address atomics per warp made this kernel wait for the L2's atomic unit)
+    __shared__ uint32_t s_cnt[8], s_base;
     const unsigned mask = __ballot_sync(0xffffffffu, live);
-    if (mask == 0) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0)
     {
-        base = atomicAdd(q.count, (uint32_t)__popc(mask));
-        atomicAdd(ray_counters + 0, (unsigned long long)__popc(mask));
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+        {
+            const uint32_t c = s_cnt[w];
+            s_cnt[w] = total;
+            total += c;
+        }
+        s_base = total ? atomicAdd(q.count, total) : 0u;
+        if (total) atomicAdd(ray_counters + 0, (unsigned long long)total);
     }
-    base = __shfl_sync(0xffffffffu, base, leader);
+    __syncthreads();
     if (!live) return;
     const float4 rot = st.ro_t[idx];
-    float4* dst = (float4*)q.rays + ((size_t)base + (size_t)__popc(mask & ((1u << lane) - 1u))) * 2;
+    float4* dst = (float4*)q.rays + ((size_t)s_base + s_cnt[warp] + (size_t)__popc(mask & ((1u << lane) - 1u))) * 2;
     dst[0] = make_float4(rot.x, rot.y, rot.z, __uint_as_float((uint32_t)idx));
     dst[1] = make_float4(rdp.x, rdp.y, rdp.z, 0.0f);
 }
@@ -261,10 +271,35 @@ __global__ void __launch_bounds__(256)
             st.rng[idx] = rng.state;
             emits = !own_triangle_stops(org, dir, tri_at(tris60, prim));
         }
-        uint32_t stride = 0;
-        const uint32_t slot = reserve_rays(q, emits, 1u, stride);
-        if (emits) put_ray(q, slot, org, dir, (uint32_t)idx, 0u);
-        traced = emits ? 1u : 0u;
+        // one reservation and one update of each ray counter per block (three same-address atomics per warp made this kernel
+        // wait for the L2's atomic unit: a launch is ~0.1 ms long and has 65 k warps)
+        __shared__ uint32_t s_cnt[8], s_dec[8], s_base;
+        const unsigned mask = __ballot_sync(0xffffffffu, emits), dmask = __ballot_sync(0xffffffffu, lit && !emits);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0)
+        {
+            s_cnt[warp] = (uint32_t)__popc(mask);
+            s_dec[warp] = (uint32_t)__popc(dmask);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            uint32_t total = 0, dec = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++)
+            {
+                const uint32_t c = s_cnt[w];
+                s_cnt[w] = total;
+                total += c;
+                dec += s_dec[w];
+            }
+            s_base = total ? atomicAdd(q.count, total) : 0u;
+            if (total) atomicAdd(ray_counters + 1, (unsigned long long)total);
+            if (dec) atomicAdd(ray_counters + 2, (unsigned long long)dec);  // crt_rays_decided_at_emission
+        }
+        __syncthreads();
+        if (emits) put_ray(q, s_base + s_cnt[warp] + (uint32_t)__popc(mask & ((1u << lane) - 1u)), org, dir, (uint32_t)idx, 0u);
+        return;  // counted above
     }
     else
     {
