@@ -51,6 +51,7 @@ extern "C" int crt_init(int device, crt_ctx** out)
     if (const char* e = getenv("CRT_LIGHT_TABLE")) ctx->light_table = atoi(e);
     if (const char* e = getenv("CRT_RESOLVE_REUSE")) ctx->resolve_reuse = atoi(e);
     if (const char* e = getenv("CRT_POOLED_CLOSEST")) ctx->pooled_closest = atoi(e);
+    if (const char* e = getenv("CRT_RAYCAST_HINT")) ctx->raycast_hint = atoi(e);
     *out = ctx;
     return CRT_OK;
 }
@@ -161,6 +162,9 @@ extern "C" int crt_malloc(crt_ctx* ctx, size_t bytes, void** out)
     CRT_REQUIRE(ctx && out, "null argument");
     CRT_CUDA(cudaSetDevice(ctx->device));
     CRT_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+    // zeroed: crt_raycast reads the Visibility record of every pixel before it writes it (the hint of px_raycast_hinted —
+    // any content is a valid hint, but memory of the library's own making should not be read uninitialised)
+    CRT_CUDA(cudaMemset(*out, 0, bytes ? bytes : 16));
     return CRT_OK;
 }
 extern "C" int crt_free(crt_ctx* ctx, void* p)

@@ -502,13 +502,15 @@ CRT_HD int walk_step(const Bvh& bvh, Walk& w, WalkStack& st, const RaySetup& r, 
 // Closest hit (ANY = false) in [tmin, tmax]: smallest t, ties -> larger primitive id.
 // Any hit (ANY = true): returns at the first accepted triangle; only hit.prim >= 0 is meaningful.
 // FAR_FIRST (any-hit only): see setup_ray.
+// trace_seeded: the same walk started from a hit the caller already holds (hit.prim >= 0, hit.t its distance; or
+// hit.prim = -1 and hit.t = tmax for none).  The walk culls with hit.t from its first node on and replaces the seed by
+// any triangle that beats it under the tie rule, so the result is the unseeded walk's as long as the seed is what
+// ray_triangle() returns for a triangle of this tree (when the walk meets that triangle again it computes the same t and
+// the same id, which replaces nothing).
 template <bool ANY, bool FAR_FIRST = false>
-CRT_HD bool trace(const Bvh& bvh, f3 ro, f3 rd, float tmin, float tmax, Hit& hit)
+CRT_HD bool trace_seeded(const Bvh& bvh, f3 ro, f3 rd, float tmin, Hit& hit)
 {
     static_assert(ANY || !FAR_FIRST, "a closest-hit walk visits near children first");
-    hit.prim = -1;
-    hit.t = tmax;
-    hit.u = hit.v = 0.0f;
     const RaySetup r = setup_ray(ro, rd, FAR_FIRST);
 #if !defined(CRT_WALK_SPLIT_OBJECTS)
     // Stack and scalars as members of one object: the compiler then keeps the scalars in local memory too — more
@@ -535,5 +537,13 @@ CRT_HD bool trace(const Bvh& bvh, f3 ro, f3 rd, float tmin, float tmax, Hit& hit
         if (state != kWalkContinue) break;
     }
     return hit.prim >= 0;
+}
+template <bool ANY, bool FAR_FIRST = false>
+CRT_HD bool trace(const Bvh& bvh, f3 ro, f3 rd, float tmin, float tmax, Hit& hit)
+{
+    hit.prim = -1;
+    hit.t = tmax;
+    hit.u = hit.v = 0.0f;
+    return trace_seeded<ANY, FAR_FIRST>(bvh, ro, rd, tmin, hit);
 }
 }  // namespace crt

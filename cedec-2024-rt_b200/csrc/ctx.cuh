@@ -23,6 +23,8 @@ struct crt_ctx
     void* queue_rays = nullptr;
     unsigned* queue_counters = nullptr;
     size_t queue_capacity = 0;
+    int raycast_hint = 1;  // primary rays seeded with the triangle the pixel's Visibility record names before the call (CRT_RAYCAST_HINT=0: off)
+    const void* hint_tris = nullptr;  // the triangle array a crt_raycast of this context has seen to be the tree's own (licence for the prefetch's hints)
     int pooled_closest = 1;  // examples 07-09: closest hits through the persistent pooled kernel (CRT_POOLED_CLOSEST: 0 never, 1 bounce rays, 2 all)
     void* path_state = nullptr;  // examples 07-09 as a wavefront: per-path state (kernels_paths.cu)
     size_t path_state_pixels = 0;

@@ -16,6 +16,14 @@ __global__ void __launch_bounds__(256) k_raycast(int W, int H, Rows rows, Bvh bv
     const TilePix t = this_pixel(W, H, rows);
     if (t.in) px_raycast(t.px, W, H, bvh, raygen, vis);
 }
+// the same rays, each walk seeded with the triangle the pixel's record names before the call (restir_pixel.cuh:
+// px_raycast_hinted); launched when the host hands in the triangle array the tree was built over
+__global__ void __launch_bounds__(256) k_raycast_hinted(int W, int H, Rows rows, Bvh bvh, crt_raygen raygen, crt_visibility* vis,
+                                                        const float* tris60, uint32_t n_tris)
+{
+    const TilePix t = this_pixel(W, H, rows);
+    if (t.in) px_raycast_hinted(t.px, W, H, bvh, raygen, vis, tris60, n_tris);
+}
 // WF: emit the visibility-reuse ray into the queue instead of walking it here (shadow_queue.cuh)
 // SH: use_shadowed_target_function may be set (traversal code inside the target function); the common SH = false
 // instantiation has none, which takes the walk's stack and ~40 registers out of the reservoir kernels
@@ -219,6 +227,7 @@ int preload_dropin_kernels()
 {
     cudaFuncAttributes a;
     CRT_CUDA(cudaFuncGetAttributes(&a, k_raycast));
+    CRT_CUDA(cudaFuncGetAttributes(&a, k_raycast_hinted));
     CRT_CUDA(cudaFuncGetAttributes(&a, k_tone_mapping<0>));
     CRT_CUDA(cudaFuncGetAttributes(&a, k_tone_mapping<1>));
     CRT_CUDA(cudaFuncGetAttributes(&a, k_clear));
@@ -235,9 +244,18 @@ extern "C" int crt_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_bu
     CRT_REQUIRE(ctx && geom, "null context or geometry");
     CRT_CHECK_IMAGE(W, H);
     CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
-    (void)triangles;  // the reference's raycast does not read it either (10_restir_di.cu:9-34)
-    k_raycast<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), geom->view(), raygen,
-                                                       (crt_visibility*)visibility_buffer.data);
+    // The reference's raycast does not read `triangles` (10_restir_di.cu:9-34).  Here it is the licence for the hinted walk:
+    // when it is the very array the tree was built over, the record each pixel already holds seeds its walk.
+    if (ctx->raycast_hint && triangles.data != nullptr && triangles.data == (const void*)geom->src && geom->n_tris)
+    {
+        ctx->hint_tris = geom->src;
+        k_raycast_hinted<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), geom->view(), raygen,
+                                                                  (crt_visibility*)visibility_buffer.data,
+                                                                  (const float*)geom->src, (uint32_t)geom->n_tris);
+    }
+    else
+        k_raycast<<<tile_grid(W, rows_of(ctx, H)), 256, 0, ctx->stream>>>(W, H, rows_of(ctx, H), geom->view(), raygen,
+                                                           (crt_visibility*)visibility_buffer.data);
     return check_launch(ctx, "raycast");
 }
 
@@ -262,6 +280,7 @@ extern "C" int crt_restir_prefetch_raycast(crt_ctx* ctx, int W, int H, crt_geome
         ctx->vis_next = nullptr;
         ctx->vis_next_pixels = 0;
         CRT_CUDA(cudaMalloc(&ctx->vis_next, n * sizeof(crt_visibility)));
+        CRT_CUDA(cudaMemsetAsync(ctx->vis_next, 0xff, n * sizeof(crt_visibility), ctx->head_stream));  // index -1: no hint yet
         ctx->vis_next_pixels = n;
     }
     if (ctx->vis_consumed_pending)  // the frame in flight may still be copying the previous prefetch out of the buffer
@@ -270,7 +289,13 @@ extern "C" int crt_restir_prefetch_raycast(crt_ctx* ctx, int W, int H, crt_geome
         ctx->vis_consumed_pending = false;
     }
     const Rows rows = rows_of(ctx, H);
-    k_raycast<<<tile_grid(W, rows), 256, 0, ctx->head_stream>>>(W, H, rows, geom->view(), raygen, (crt_visibility*)ctx->vis_next);
+    // hinted when a frame of this context has shown the tree's own triangle array to be alive (crt_raycast above); the
+    // buffer is the context's own and holds the previous prefetch, or index -1 everywhere after its allocation
+    if (ctx->raycast_hint && ctx->hint_tris != nullptr && ctx->hint_tris == (const void*)geom->src && geom->n_tris)
+        k_raycast_hinted<<<tile_grid(W, rows), 256, 0, ctx->head_stream>>>(W, H, rows, geom->view(), raygen, (crt_visibility*)ctx->vis_next,
+                                                                           (const float*)geom->src, (uint32_t)geom->n_tris);
+    else
+        k_raycast<<<tile_grid(W, rows), 256, 0, ctx->head_stream>>>(W, H, rows, geom->view(), raygen, (crt_visibility*)ctx->vis_next);
     const int rc = check_launch(ctx, "raycast", ctx->head_stream);
     if (rc != CRT_OK) return rc;
     CRT_CUDA(cudaEventRecord(ctx->ev_ray_ready, ctx->head_stream));

@@ -104,6 +104,13 @@ static int queue_trace(crt_ctx* ctx, crt_geometry geom, const ShadowQueue& q, co
     {
         CRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_shadow_queue<EPI>, kShadowWarps * 32, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
+        // tuning hook: fewer resident blocks per SM for the resolve tracer (which runs beside the next frame's head when
+        // frames overlap) or for the others — leaves room for the kernels of the other streams
+        if (const char* e = getenv(EPI == kEpiResolve ? "CRT_RESOLVE_BLOCKS_PER_SM" : "CRT_TRACE_BLOCKS_PER_SM"))
+        {
+            const int v = atoi(e);
+            if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v;
+        }
     }
     cudaStream_t st = on ? on : ctx->stream;
     k_trace_shadow_queue<EPI><<<blocks_per_sm * ctx->sm_count, kShadowWarps * 32, 0, st>>>(geom->view(), q, sink);

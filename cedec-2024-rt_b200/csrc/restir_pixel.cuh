@@ -93,6 +93,37 @@ CRT_HD void px_raycast(const Pix& px, int W, int H, const Bvh& bvh, const crt_ra
     trace<false>(bvh, ro, rd, 0.0f, kFltMax, h);
     store_vis(vis, px.idx, h);
 }
+// The same with a HINT: the primitive id the Visibility record of this pixel holds before the call — last frame's answer
+// when the host traces into the same buffer every frame, anything at all otherwise — names a triangle that is tested
+// first, with the reference's own test on the tree's own vertex bits (`tris60` is the array the tree was built over), and
+// a hit seeds the walk (bvh.cuh: trace_seeded).  The closest hit is decided by (t, primitive id) alone, so the stored
+// record is the unhinted walk's bit for bit whatever the hint was; a good hint lets the walk cull with the final distance
+// from its first node on (lab, config 5: 13.8 -> 12.0 node steps per primary ray with an unmoved camera).
+CRT_HD void px_raycast_hinted(const Pix& px, int W, int H, const Bvh& bvh, const crt_raygen& raygen, crt_visibility* vis,
+                              const float* tris60, uint32_t n_tris)
+{
+    f3 ro, rd;
+    primary_ray(raygen, px, W, H, ro, rd);
+    Hit h;
+    h.prim = -1;
+    h.t = kFltMax;
+    h.u = h.v = 0.0f;
+    const uint32_t old = (uint32_t)vis[px.idx].index;
+    if (old < n_tris)
+    {
+        const TriRef tri = tri_at(tris60, (int)old);
+        float t, u, v;
+        if (ray_triangle(ro, rd, 0.0f, kFltMax, tri.v(0), tri.v(1), tri.v(2), t, u, v))
+        {
+            h.t = t;
+            h.u = u;
+            h.v = v;
+            h.prim = (int)old;
+        }
+    }
+    trace_seeded<false>(bvh, ro, rd, 0.0f, h);
+    store_vis(vis, px.idx, h);
+}
 
 // A shadow ray the caller traces later (wavefront mode, shadow_queue.cuh): check_visibility's segment
 // (raytrace.hpp:45-52) — origin p0 + 1e-3 n0, direction p1 - p0, t in [0, 0.99].

@@ -228,6 +228,27 @@ int main(int argc, char** argv)
         cache_report("vr <- prev vr (+prev rs)", vr_full, vrp_full, &rsp_full);
         cache_report("rs <- prev rs (+this vr)", rs_full, rsp_full, &vr_full);
     }
+    // ray identity across frames: a resolve (visibility-reuse) ray of the last frame whose origin and direction are, bit for
+    // bit, those of the same pixel's ray of the same class one frame earlier has that ray's answer
+    if (frames >= 2)
+    {
+        auto same = [](const RayRec& a, const RayRec& b) { return a.pix >= 0 && b.pix >= 0 && memcmp(&a.o, &b.o, 12) == 0 && memcmp(&a.d, &b.d, 12) == 0; };
+        size_t n_rs = 0, id_rs = 0, n_vr = 0, id_vr = 0, id_rs_vr = 0;
+        double w_all = 0, w_same = 0;
+        for (size_t i = 0; i < rs_full.size(); i++)
+        {
+            if (rs_full[i].pix >= 0)
+            {
+                n_rs++;
+                w_all += rs_full[i].nodes;
+                if (same(rs_full[i], rsp_full[i])) { id_rs++; w_same += rs_full[i].nodes; }
+                else if (same(rs_full[i], vrp_full[i])) id_rs_vr++;
+            }
+            if (vr_full[i].pix >= 0) { n_vr++; if (same(vr_full[i], vrp_full[i])) id_vr++; }
+        }
+        printf("ray identity: resolve rays equal to the previous frame's resolve ray of the pixel %.1f%% (%.1f%% of their node steps), to its visibility-reuse ray %.1f%%; visibility-reuse rays equal to the previous one %.1f%%\n",
+               100.0 * id_rs / (n_rs ? n_rs : 1), 100.0 * w_same / (w_all ? w_all : 1), 100.0 * id_rs_vr / (n_rs ? n_rs : 1), 100.0 * id_vr / (n_vr ? n_vr : 1));
+    }
     // neighbourhood cache: occluder of the pixel to the left in the same frame and class
     {
         size_t occ = 0, hit = 0;

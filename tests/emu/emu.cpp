@@ -268,6 +268,12 @@ extern "C"
         const Bvh bvh = ((EmuGeom*)gp)->view();
         launch(W, H, [&](Pix p) { px_raycast(p, W, H, bvh, *rg, vis); });
     }
+    // the hinted form (restir_pixel.cuh: px_raycast_hinted): `vis` holds the hints on entry, the answers on return
+    void emu_raycast_hinted(int W, int H, void* gp, const crt_triangle* tris, int n_tris, const crt_raygen* rg, crt_visibility* vis)
+    {
+        const Bvh bvh = ((EmuGeom*)gp)->view();
+        launch(W, H, [&](Pix p) { px_raycast_hinted(p, W, H, bvh, *rg, vis, (const float*)tris, (uint32_t)n_tris); });
+    }
     void orc_generate_candidate(int W, int H, int frame, void* gp, const crt_triangle* tris, int,
                                 const crt_visibility* vis, const float* eye, const uint32_t* lights, int nlights,
                                 const crt_options* opt, crt_reservoir* res)

@@ -191,6 +191,51 @@ def test_refit_after_moving_vertices(emu, port):
     emu.geom_free(ge)
 
 
+def test_hinted_raycast_equals_the_plain_walk_for_any_hint(emu, port):
+    """px_raycast_hinted (the walk seeded with the triangle the pixel's record names before the call): the stored record is
+    the oracle's whatever the hint — the right triangle, a neighbour's, a random one, -1, garbage — also when the camera
+    moves between the frame that wrote the hints and the frame that reads them, and with duplicated triangles (ties on t
+    go to the larger id: a hint with the smaller id of a duplicate pair must not survive)"""
+    tris = small_scene("blocks_ao").copy()
+    tris = np.concatenate([tris, tris[500:700]])  # duplicates: equal t, larger id wins
+    W, H = 128, 72
+    ge = emu.geom_build(tris)
+    g = port.geom_build(tris)
+    L = emu.lib
+    L.emu_raycast_hinted.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11)
+    rg0 = port.lookat(*CAM_AO, W, H)
+    want0 = port.raycast(W, H, g, tris, rg0)
+    rg1 = port.lookat((7.0, 9.0, 8.5), (0.5, 0.0, -0.5), W, H)
+    want1 = port.raycast(W, H, g, tris, rg1)
+    assert (want0["index"] >= 0).sum() > 1000 and not same(want0["index"], want1["index"])
+    assert (want0["index"] >= len(tris) - 200).sum() > 0  # some pixels see a duplicated triangle (and report the larger id)
+
+    def run(rg, hints):
+        vis = np.zeros(W * H, dtype=want0.dtype)
+        vis["index"] = hints
+        vis["uv"] = rng.uniform(-5, 5, (W * H, 2)).astype(np.float32)
+        L.emu_raycast_hinted(W, H, ge, tris.ctypes.data, len(tris), rg.ctypes.data, vis.ctypes.data)
+        return vis
+
+    n = len(tris)
+    hint_sets = {
+        "own answer": want0["index"].copy(),
+        "other camera's answer": want1["index"].copy(),
+        "shifted by one pixel": np.roll(want0["index"], 1),
+        "random triangles": rng.integers(0, n, W * H).astype(np.int32),
+        "none": np.full(W * H, -1, np.int32),
+        "garbage": rng.integers(-2**31, 2**31 - 1, W * H).astype(np.int32),
+        "the duplicate with the smaller id": np.where(want0["index"] >= n - 200, want0["index"] - (n - 200) + 500, want0["index"]).astype(np.int32),
+    }
+    for name, hints in hint_sets.items():
+        for rg, want in ((rg0, want0), (rg1, want1)):
+            got = run(rg, hints)
+            assert same(got["index"], want["index"]) and same(got["uv"], want["uv"]), name
+    port.geom_free(g)
+    emu.geom_free(ge)
+
+
 # ---------------------------------------------------------------------------------------------- fused frame
 class EmuFusedFrame:
     """Drives emu_restir_frame_fast (the kernel sequence of crt_restir_di_frame, csrc/kernels_fast.cu) on planar

@@ -147,6 +147,39 @@ def test_raycast_bit_exact(dev, port, scene, cam, size):
     assert (outs[1]["_pad"] == 0).all()
 
 
+def test_raycast_is_the_oracle_s_whatever_the_buffer_held(dev, port):
+    """crt_raycast seeds each pixel's walk with the triangle its Visibility record names before the call (px_raycast_hinted):
+    the result does not depend on it — own answers, another camera's, random ids, -1, garbage, the smaller id of a duplicate"""
+    tris = small_scene("blocks_ao").copy()
+    tris = np.concatenate([tris, tris[500:700]])
+    W, H = 320, 180
+    g, gp = dev.geom_build(tris), port.geom_build(tris)
+    rt, c = dev.rt, dev.c
+    rng = np.random.default_rng(5)
+    rg0, rg1 = dev.lookat(*CAM_AO, W, H), dev.lookat((7.0, 9.0, 8.5), (0.5, 0.0, -0.5), W, H)
+    want = [port.raycast(W, H, gp, tris, port.lookat(*CAM_AO, W, H)), port.raycast(W, H, gp, tris, port.lookat((7.0, 9.0, 8.5), (0.5, 0.0, -0.5), W, H))]
+    n = len(tris)
+    assert (want[0]["index"] >= n - 200).sum() > 0
+    hint_sets = {
+        "own answer": want[0]["index"].copy(),
+        "other camera's answer": want[1]["index"].copy(),
+        "random triangles": rng.integers(0, n, W * H).astype(np.int32),
+        "none": np.full(W * H, -1, np.int32),
+        "garbage": rng.integers(-2**31, 2**31 - 1, W * H).astype(np.int32),
+        "the duplicate with the smaller id": np.where(want[0]["index"] >= n - 200, want[0]["index"] - (n - 200) + 500, want[0]["index"]).astype(np.int32),
+    }
+    for name, hints in hint_sets.items():
+        for k, rg in enumerate((rg0, rg1)):
+            vis = np.zeros(W * H, c.VISIBILITY)
+            vis["index"] = hints
+            d = rt.to_device(vis)
+            rt.raycast(W, H, g, g.triangles, dev._rg(rg), d)
+            got = d.to_host()
+            assert same(got["index"], want[k]["index"]) and same(got["uv"], want[k]["uv"]), name
+    dev.geom_free(g)
+    port.geom_free(gp)
+
+
 def test_raycast_blocks_restir_1080p_pixel_classes(dev, port):
     """config 4/5 camera on the real scene: bit-exact primitive ids against the oracle on a band of rows, and
     the pixel-class counts SURVEY.md section 4 extracted from the reference for the whole frame"""
