@@ -22,6 +22,9 @@ __global__ void __launch_bounds__(256) k_raycast_hinted(int W, int H, Rows rows,
                                                         const float* tris60, uint32_t n_tris)
 {
     const TilePix t = this_pixel(W, H, rows);
+    // a seeded walk accepts (almost) no triangle any more, and triangle postponing — which waits for more lanes before it
+    // runs the test — only delays it: 1.695 -> 1.672 ms without (profiles/r2/tuning.txt, batch 33)
+    bvh.postpone_ratio = 0.0f;
     if (t.in) px_raycast_hinted(t.px, W, H, bvh, raygen, vis, tris60, n_tris);
 }
 // WF: emit the visibility-reuse ray into the queue instead of walking it here (shadow_queue.cuh)
