@@ -164,7 +164,11 @@ extern "C" int crt_malloc(crt_ctx* ctx, size_t bytes, void** out)
     CRT_CUDA(cudaMalloc(out, bytes ? bytes : 16));
     // zeroed: crt_raycast reads the Visibility record of every pixel before it writes it (the hint of px_raycast_hinted —
     // any content is a valid hint, but memory of the library's own making should not be read uninitialised)
-    CRT_CUDA(cudaMemset(*out, 0, bytes ? bytes : 16));
+    // On the context's stream and waited for: a plain cudaMemset runs on the legacy default stream, asynchronously for
+    // device memory, and the context's non-blocking streams do not order themselves after it — it zeroed the tail of a
+    // freshly uploaded triangle array in tests/test_gpu_configs.py (GPU batch 34).
+    CRT_CUDA(cudaMemsetAsync(*out, 0, bytes ? bytes : 16, ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(ctx->stream));
     return CRT_OK;
 }
 extern "C" int crt_free(crt_ctx* ctx, void* p)
