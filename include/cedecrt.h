@@ -192,7 +192,11 @@ int crt_trace_closest_brute(crt_ctx* ctx, const crt_triangle* d_triangles, size_
 /* ---- kernels: one export per reference KERNEL, parameter lists verbatim (same order, same by-value
  * structs); grid/block are implied (the reference always launches ceil(W*H/256) x 256).
  * Reservoir / Visibility buffers are the reference's AoS layouts ("drop-in mode"). */
-/* examples/10_restir_di/10_restir_di.cu:9-34 */
+/* examples/10_restir_di/10_restir_di.cu:9-34.  When `triangles` is the array `geom` was built over, every pixel's walk
+ * is first seeded with the triangle its record in `visibility_buffer` names on entry (last frame's answer for a host
+ * that traces into the same buffer every frame; any content is allowed and none changes the result, which is the
+ * exhaustive loop's closest hit bit for bit).  That array must then stay alive as long as `geom` is in use, as for
+ * crt_refit_geometry.  CRT_RAYCAST_HINT=0 in the environment turns the seeding off. */
 int crt_raycast(crt_ctx* ctx, int width, int height, crt_geometry geom, crt_buffer triangles, crt_raygen raygen,
                 crt_buffer visibility_buffer);
 /* 10_restir_di.cu:36-135 */
