@@ -416,6 +416,51 @@ CRT_HD Res ris_candidates_shadowed(const Bvh& bvh, const L& lights, const Surf& 
     return r;
 }
 
+// DEFERRED SELECTION.  Reservoir::update copies the whole sample (hit position, hit normal, radiance, origin position,
+// origin normal: 15 floats) whenever a candidate is accepted — in SIMT code 14 predicated moves per candidate, executed
+// whether or not the lane accepts, and 15 registers that live across the loop.  The sample is a pure function of the
+// candidate's three randoms (light pick, two barycentric randoms), so the loop only remembers those of the candidate
+// accepted last and the sample is built once, after the loop, by the very calls that built it inside (fetch + finish:
+// the same record, the same operations, the same bits).
+// MEASURED AND REJECTED (profiles/r2/tuning.txt, batch 37; kept behind -DCRT_RIS_DEFERRED): the loop shrinks from 433 to
+// 410 SASS instructions per two candidates, bit-identical — and k_candidate_temporal goes from 2.027 to 2.053 ms.  The
+// kernel is bound by the L1's wavefronts for the light-record gathers (l1tex at 85 % of peak), not by issue slots: the
+// instructions saved were free, the 33rd gather per pixel is not.  (At 4 blocks per SM, which the smaller live set
+// allows with 48 bytes of spills: 2.029 ms; with three records in flight: 2.226 ms.)
+struct RisPick
+{
+    float r0, r1, r2;
+    bool has;
+};
+template <class L>
+CRT_HD void ris_update_pick(const Bvh& bvh, const Surf& surf, const LightSample& ls, float inv_n, float u, bool shadowed,
+                            float r0, float r1, float r2, Res& r, RisPick& pick)
+{
+    const float p_hat = target_function(bvh, surf.p, surf.n, ls.p, ls.n, ls.emissive, shadowed);
+    const float weight = p_hat / (L::kHasPdf ? ls.pdf : inv_n * 1.0f / ls.area);  // ris_apply_pdf / ris_apply
+    r.w_sum += weight;
+    r.M += 1;
+    if (u < weight / r.w_sum)
+    {
+        pick.r0 = r0;
+        pick.r1 = r1;
+        pick.r2 = r2;
+        pick.has = true;
+    }
+}
+template <class L>
+CRT_HD void ris_pick_finish(const L& lights, const Surf& surf, const RisPick& pick, Res& r)
+{
+    if (!pick.has) return;
+    const LightSample ls = lights.finish(lights.fetch(pick.r0, 0u), pick.r1, pick.r2);
+    r.s.hp = ls.p;
+    r.s.hn = ls.n;
+    r.s.rad = ls.emissive;
+    r.s.op = surf.p;
+    r.s.on = surf.n;
+    r.s.vis = 0;
+}
+
 template <class L>
 CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int count, bool shadowed, Pcg& rng,
                           unsigned pair_mask = 0u)
@@ -426,6 +471,36 @@ CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int
     Res r = empty_res();
     const float inv_n = 1.0f / (float)lights.n;
     int i = 0;
+#if defined(CRT_RIS_DEFERRED)
+    RisPick pick{0.0f, 0.0f, 0.0f, false};
+    for (; i + kRisBatch <= count; i += kRisBatch)
+    {
+        typename L::Raw raw[kRisBatch];
+        float r0[kRisBatch], r1[kRisBatch], r2[kRisBatch], u[kRisBatch];
+#pragma unroll
+        for (int b = 0; b < kRisBatch; ++b)
+        {
+            r0[b] = rng.next_f();
+            r1[b] = rng.next_f();
+            r2[b] = rng.next_f();
+            u[b] = rng.next_f();
+            raw[b] = lights.fetch(r0[b], pair_mask);
+        }
+#pragma unroll
+        for (int b = 0; b < kRisBatch; ++b)
+            ris_update_pick<L>(bvh, surf, lights.finish(raw[b], r1[b], r2[b]), inv_n, u[b], shadowed, r0[b], r1[b], r2[b], r, pick);
+    }
+    for (; i < count; ++i)
+    {
+        const float r0 = rng.next_f();
+        const float r1 = rng.next_f();
+        const float r2 = rng.next_f();
+        const float u = rng.next_f();
+        ris_update_pick<L>(bvh, surf, lights.finish(lights.fetch(r0, pair_mask), r1, r2), inv_n, u, shadowed, r0, r1, r2, r, pick);
+    }
+    ris_pick_finish(lights, surf, pick, r);
+    return r;
+#else
     for (; i + kRisBatch <= count; i += kRisBatch)
     {
         typename L::Raw raw[kRisBatch];
@@ -451,6 +526,7 @@ CRT_HD Res ris_candidates(const Bvh& bvh, const L& lights, const Surf& surf, int
         ris_update<L>(bvh, surf, lights.finish(lights.fetch(r0, pair_mask), r1, r2), inv_n, u, shadowed, r);
     }
     return r;
+#endif
 }
 
 // temporal_resampling body (10_restir_di.cu:172-233): `r` is this frame's reservoir, `prev` last frame's.
