@@ -559,6 +559,13 @@ def run_cuda(args):
                 # (clamped: for a 0.1 ms kernel the event-to-event time of the profile pass can come out a little shorter
                 # than its instructions allow at the sampled clock)
                 k["issue_frac"] = min(1.0, round(inst / (k["ms_per_launch"] * 1e-3) / issue_peak, 4))
+        # k_candidate_temporal against the roof that bounds it: one L1 wavefront per lane and 256-bit
+        # load of its 32 random 64-byte light records (every lane its own 128-byte line), one wavefront per SM and clock
+        if "candidate_temporal" in kern and world == 1:
+            k = kern["candidate_temporal"]
+            wavefronts = n_diffuse * 32 * 2
+            k["l1_wavefronts_per_launch"] = int(wavefronts)
+            k["l1_wavefront_frac"] = round(wavefronts / sm_count / (sm_mhz * 1e6) / (k["ms_per_launch"] * 1e-3), 4)
         frame_ms_by_kernel = {k: v["ms_per_launch"] * v["launches_per_frame"] for k, v in kern.items()}
         dominant = max(frame_ms_by_kernel, key=frame_ms_by_kernel.get)
         passes = [k for k in kern if k in HBM_BOUND]
