@@ -353,9 +353,11 @@ extern "C" int crt_restir_frame_begin(crt_ctx* ctx, int W, int H, int frame, crt
     }
     if (ctx->prev_cam_set)
     {
-        // a look-up at another pixel reads rows this context may not compute or hold
-        CRT_REQUIRE(!ctx->links_set && ctx->row_begin <= 0 && (ctx->row_end < 0 || ctx->row_end >= H),
-                    "temporal reprojection in the fused frame needs the whole image on one context");
+        // A look-up at another pixel reads rows this context may not compute.  A host that renders a
+        // row range gathers every slab's rows of `temporal` before this call (python/slabs.py: gather_history); the
+        // direct-store links mirror the 87 halo rows only, so they cannot serve it.
+        CRT_REQUIRE(!ctx->links_set, "temporal reprojection in the fused frame cannot run over the direct-store slab links: "
+                                     "the host gathers the history rows (exchange mode)");
     }
     if (!fused(options))
     {

@@ -89,6 +89,12 @@ def halo_plan(H, edges, rank, halo=HALO):
     return plan
 
 
+def full_plan(H, edges, rank):
+    """the halo plan with an unbounded reach: every rank sends all its rows to every other rank and receives all of
+    theirs (the history gather of temporal reprojection, SlabRenderer.gather_history)"""
+    return halo_plan(H, edges, rank, halo=H)
+
+
 def row_byte_ranges(W, H, rows, layout):
     """byte ranges [(begin, end)] that image rows [a, b) occupy in a bottom-up buffer.
     layout: ("aos", elem_bytes) — one contiguous range; ("planes", [elem_bytes...]) — planar storage over W*H
@@ -141,14 +147,19 @@ class SlabRenderer:
     tensors, so that torch.distributed can move halo rows; kernels run through the C ABI on torch's stream."""
 
     def __init__(self, torch, dist, rank, world, tris, cam, W, H, fused=True, edges=None, options=None, p2p=True,
-                 stream=None, share=None, connect=True, overlap=False):
+                 stream=None, share=None, connect=True, overlap=False, reproject=False):
         """p2p: in fused mode with more than one rank, exchange halo rows by direct peer stores (csrc/slab_p2p.cu,
         buffers shared through cudaIpc handles) instead of NCCL send/recv; needs slabs >= HALO rows, W % 16 == 0.
         stream: the torch stream this slab's kernels go to (default: the current one).  share: another SlabRenderer on
         the same GPU whose scene, light list and BVH this one uses instead of uploading and building its own.
         connect=False leaves the neighbour links to the caller (SlabGroup: slabs of one process are linked by plain
         pointers, `rank`/`world` then count slabs, not processes).  overlap: fused mode only — the frame's tail (resolve
-        rays + tone mapping) runs on the context's second stream beside the next frame's head (crt_set_frame_overlap)."""
+        rays + tone mapping) runs on the context's second stream beside the next frame's head (crt_set_frame_overlap).
+        reproject (extension): temporal resampling looks the history up at the pixel the surface point
+        had in the previous frame's camera (set_camera).  That pixel may lie in any slab — the displacement is bounded by the
+        camera motion, not by the spatial halo — so before such a frame every rank receives every other rank's rows of the
+        history (full_plan: the halo plan with an unbounded reach, over NCCL / gloo); the direct-store path mirrors halo
+        rows only and is not used."""
         import numpy as np
 
         import cedecrt
@@ -166,6 +177,9 @@ class SlabRenderer:
         self.stream = stream if stream is not None else torch.cuda.current_stream()
         assert self.stream.cuda_stream != 0, "bench needs a non-default torch stream"
         self.rt.set_stream(self.stream.cuda_stream)
+        self.reproject, self.prev_raygen = bool(reproject), None
+        if self.reproject:
+            p2p = False
         self.overlap = bool(overlap and self.fused)
         self._tail = None
         if self.overlap:
@@ -174,6 +188,7 @@ class SlabRenderer:
         self.edges = edges if edges is not None else [slab_rows(H, world, r)[0] for r in range(world)] + [H]
         self.y0, self.y1 = self.edges[rank], self.edges[rank + 1]
         self.plan = halo_plan(H, self.edges, rank, self.halo) if world > 1 else []
+        self.full_plan = full_plan(H, self.edges, rank) if world > 1 else []
         self.rt.set_row_range(self.y0, self.y1)
         self.eye = tuple(float(np.float32(v)) for v in cam[0])
         self.raygen = cedecrt.lookat(cam[0], cam[1], W, H)
@@ -367,6 +382,21 @@ class SlabRenderer:
         if self.world > 1:
             self.halo_bytes += exchange(self.dist, t, self.W, self.H, layout, self.plan)
 
+    def set_camera(self, eye, lookat_pt):
+        """a new camera for the frames that follow; with reproject=True the camera of the last frame rendered is what the
+        next frame's history look-up inverts (cedecrt.RestirDI.set_camera, one slab)"""
+        import numpy as np
+
+        self.eye = tuple(float(np.float32(v)) for v in eye)
+        self.raygen = self.c.lookat(eye, lookat_pt, self.W, self.H)
+        self.rt.clear(self.accumulation, self.W, self.H)  # 10_restir_di.cpp:257-267
+
+    def gather_history(self):
+        """every rank's rows of the temporal reservoirs to every rank (reprojection reads the history anywhere)"""
+        if self.world > 1:
+            self.halo_bytes += exchange(self.dist, self.t_tmp, self.W, self.H, SOA_RESERVOIR if self.fused else AOS_RESERVOIR,
+                                        self.full_plan)
+
     def frame(self):
         rt, W, H, o, g, t, v, eye = self.rt, self.W, self.H, self.options, self.geom, self.triangles, self.visibility, self.eye
         if self.fused and self.p2p:
@@ -375,7 +405,14 @@ class SlabRenderer:
             return
         self.frame_index += 1
         f = self.frame_index
+        look_up = self.reproject and self.prev_raygen is not None and o.use_temporal_resampling
+        this_raygen = self.raygen
+        if look_up:
+            self.gather_history()
         if self.fused:
+            if self.reproject:
+                rt.restir_set_previous_camera(self.prev_raygen if look_up else None)
+                self.prev_raygen = this_raygen
             rt.restir_frame_begin(W, H, f, g, t, self.raygen, eye, self.lights, o, self.bufs)
             if self.overlap:
                 rt.restir_prefetch_raycast(W, H, g, self.raygen)  # the next frame's camera (static here)
@@ -388,7 +425,11 @@ class SlabRenderer:
         rt.raycast(W, H, g, t, self.raygen, v)
         self.exchange(self.t_vis, AOS_VISIBILITY)
         rt.generate_candidate(W, H, f, g, t, v, eye, self.lights, o, self.reservoir0)
-        rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        if look_up:
+            rt.temporal_resampling_reprojected(W, H, f, g, t, v, eye, o, self.prev_raygen, self.temporal, self.reservoir0)
+        else:
+            rt.temporal_resampling(W, H, f, g, t, v, eye, o, self.temporal, self.reservoir0)
+        self.prev_raygen = this_raygen
         rt.save_temporal_reservoir(W, H, self.reservoir0, self.temporal)
         bi, bo, ti = self.reservoir0, self.reservoir1, self.t_r0
         for k in range(o.spatial_resampling_passes):

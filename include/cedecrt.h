@@ -223,8 +223,11 @@ int crt_temporal_resampling_reprojected(crt_ctx* ctx, int width, int height, int
  * the frame's candidate + temporal kernel reads the history at the reprojected pixel — from a snapshot of `temporal`
  * the library takes at the start of the frame (72 bytes per pixel of its own; the fused merge writes `temporal` in
  * place) — and with options that take the per-kernel path the call above is used.  NULL: no reprojection (the
- * reference's behaviour, the default).  One context must hold the whole image (no row range, no slab links).  With the
- * previous camera equal to the current one the frame equals the plain fused frame bit for bit. */
+ * reference's behaviour, the default).  A context that renders a row range (crt_set_row_range) must hold every row of
+ * `temporal` the look-ups can reach: the host gathers the other contexts' rows before crt_restir_frame_begin
+ * (python/slabs.py: SlabRenderer(reproject=True).gather_history does, over NCCL); the direct-store slab links mirror
+ * the 87 halo rows only and the call refuses them.  With the previous camera equal to the current one the frame equals
+ * the plain fused frame bit for bit. */
 int crt_restir_set_previous_camera(crt_ctx* ctx, const crt_raygen* previous_raygen);
 /* 10_restir_di.cu:239-254 — note the reference's parameter names are swapped: the first buffer is the source */
 int crt_save_temporal_reservoir(crt_ctx* ctx, int width, int height, crt_buffer src, crt_buffer dst);

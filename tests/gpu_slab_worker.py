@@ -22,8 +22,11 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream())
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    mode = os.environ.get("SLAB_MODE", "fused")  # fused (direct peer stores) | fused_nccl | dropin (NCCL) | group
-    fused = mode != "dropin"
+    # fused (direct peer stores) | fused_nccl | dropin (NCCL) | group | fused_reproject | dropin_reproject (a camera that moves
+    # twice, temporal resampling with the history looked up at the reprojected pixel: every rank gathers every slab's history)
+    mode = os.environ.get("SLAB_MODE", "fused")
+    reproject = mode.endswith("_reproject")
+    fused = not mode.startswith("dropin")
     if stage_assets.have_scene("blocks_restir"):
         tris = stage_assets.load_scene("blocks_restir")
         cam, W, H = ((-0.579885, 22.194597, -6.567105), (5.224952, 20.847435, 1.431192)), 960, 540
@@ -37,9 +40,18 @@ def main():
         part = slabs.SlabGroup(torch, dist, rank, world, tris, cam, W, H, sub=2)
         part.calibrate(rounds=1, frames=1)  # uneven slabs, and a history reset in between
     else:
-        part = slabs.SlabRenderer(torch, dist, rank, world, tris, cam, W, H, fused=fused, p2p=(mode == "fused"))
-    full = slabs.SlabRenderer(torch, None, 0, 1, tris, cam, W, H, fused=fused)
-    for _ in range(3):
+        part = slabs.SlabRenderer(torch, dist, rank, world, tris, cam, W, H, fused=fused, p2p=(mode == "fused"), reproject=reproject)
+    full = slabs.SlabRenderer(torch, None, 0, 1, tris, cam, W, H, fused=fused, reproject=reproject)
+    e, c = np.asarray(cam[0], np.float64), np.asarray(cam[1], np.float64)
+    moves = {1: (tuple(e + (0.4, -0.2, 0.1)), tuple(c + (0.1, 0.0, -0.1))),  # after frame 1: most surface points stay on screen
+             2: (tuple(e + (0.9, -1.0, 0.3)), tuple(c + (0.2, 0.6, -0.2)))} if reproject else {}  # a larger, mostly vertical move
+    for k in range(3):
+        part.frame()
+        full.frame()
+        if k + 1 in moves:
+            part.set_camera(*moves[k + 1])
+            full.set_camera(*moves[k + 1])
+    if reproject:
         part.frame()
         full.frame()
     torch.cuda.synchronize()

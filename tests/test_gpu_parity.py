@@ -698,9 +698,10 @@ def test_slab_group_on_one_gpu():
                 assert torch.equal(a, b), (name, sl.rank)
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_nccl", "dropin", "group"])
+@pytest.mark.parametrize("mode", ["fused", "fused_nccl", "dropin", "group", "fused_reproject", "dropin_reproject"])
 def test_slabs_on_gpus(mode):
-    """N row slabs on N GPUs with NCCL halo exchange reproduce the single-GPU frame bit for bit (needs >= 2 GPUs)"""
+    """N row slabs on N GPUs with NCCL halo exchange reproduce the single-GPU frame bit for bit (needs >= 2 GPUs);
+    *_reproject: with a moving camera and temporal reprojection, the history rows of every slab gathered by every rank"""
     import subprocess
     import sys
 

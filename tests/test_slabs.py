@@ -117,12 +117,24 @@ def emu_lib():
     return C.CDLL(so)
 
 
-@pytest.mark.parametrize("world,height", [(2, 200), (3, 200)])
-def test_slab_frames_equal_single_process_frames_gloo(world, height, port):
+def test_full_plan_moves_every_row_to_every_rank():
+    H = 1080
+    for world in (2, 3, 8):
+        edges = [slabs.slab_rows(H, world, r)[0] for r in range(world)] + [H]
+        for r in range(world):
+            plan = slabs.full_plan(H, edges, r)
+            assert sorted(p[0] for p in plan) == [q for q in range(world) if q != r]
+            for peer, send, recv in plan:
+                assert send == (edges[r], edges[r + 1]) and recv == (edges[peer], edges[peer + 1])
+
+
+@pytest.mark.parametrize("world,height,reproject", [(2, 200, 0), (3, 200, 0), (2, 200, 1), (3, 120, 1)])
+def test_slab_frames_equal_single_process_frames_gloo(world, height, reproject, port):
     """world 2: slabs taller than the halo (the 8-GPU 4K case); world 3 at H = 200: slabs thinner than the halo, so
-    rows travel between non-adjacent ranks too"""
-    env = dict(os.environ, SLAB_H=str(height), OMP_NUM_THREADS="2")
-    port_no = 29500 + (os.getpid() % 1000) + world
+    rows travel between non-adjacent ranks too; reproject: a camera that moves twice, temporal resampling with the
+    history looked up at the reprojected pixel, every rank gathering every slab's history rows first"""
+    env = dict(os.environ, SLAB_H=str(height), OMP_NUM_THREADS="2", SLAB_REPROJECT=str(reproject))
+    port_no = 29500 + (os.getpid() % 1000) + world + 7 * reproject
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", str(port_no),
                         os.path.join(ROOT, "tests", "slab_worker.py")], env=env, capture_output=True, text=True,
