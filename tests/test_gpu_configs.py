@@ -386,11 +386,11 @@ def test_temporal_reprojection_bit_exact_with_a_moving_camera(rt, exact, port):
         app2.set_camera((8.4, 7.8, 8.1), (0.1, 0.0, -0.1))
         app2.frame()
     assert same(x.accumulation.to_host(), y.accumulation.to_host()) and same(x.temporal.to_host(), y.temporal.to_host())
-    # one context must hold the whole image
+    # a context that renders a row range may look history up as well: the host then provides the other rows of `temporal`
+    # (tests/gpu_slab_worker.py, modes *_reproject: N slabs == 1 slab); only the direct-store slab links are refused
     rt.set_row_range(8, 40)
     try:
-        with pytest.raises(cedecrt.CrtError, match="whole image"):
-            fused.frame()
+        fused.frame()
     finally:
         rt.set_row_range(0, -1)
         rt.restir_set_previous_camera(None)
