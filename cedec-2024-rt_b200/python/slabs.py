@@ -313,6 +313,7 @@ class SlabRenderer:
         self.edges = list(edges)
         self.y0, self.y1 = self.edges[self.rank], self.edges[self.rank + 1]
         self.plan = halo_plan(self.H, self.edges, self.rank, self.halo) if self.world > 1 else []
+        self.full_plan = full_plan(self.H, self.edges, self.rank) if self.world > 1 else []
         self.rt.set_row_range(self.y0, self.y1)
         self.host_pixels = self.torch.empty(4 * self.W * max(self.y1 - self.y0, 1), dtype=self.torch.uint8).pin_memory()
 
