@@ -249,6 +249,7 @@ extern "C" int crt_raycast(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_bu
     CRT_CHECK_BUF(visibility_buffer, (size_t)W * H, "visibility");
     // The reference's raycast does not read `triangles` (10_restir_di.cu:9-34).  Here it is the licence for the hinted walk:
     // when it is the very array the tree was built over, the record each pixel already holds seeds its walk.
+    if (triangles.data == nullptr || triangles.data != (const void*)geom->src) ctx->hint_tris = nullptr;
     if (ctx->raycast_hint && triangles.data != nullptr && triangles.data == (const void*)geom->src && geom->n_tris)
     {
         ctx->hint_tris = geom->src;
@@ -314,6 +315,8 @@ namespace crt
 int raycast_or_prefetched(crt_ctx* ctx, int W, int H, crt_geometry geom, crt_buffer triangles, crt_raygen raygen, crt_buffer visibility)
 {
     const Rows rows = rows_of(ctx, H);
+    // every frame renews (or withdraws) the licence for the prefetch's hints: the host has just handed in its triangle array
+    ctx->hint_tris = (triangles.data != nullptr && triangles.data == (const void*)geom->src) ? (const void*)geom->src : nullptr;
     const bool hit = ctx->ray_next_valid && ctx->ray_next_geom == geom->serial && !memcmp(&ctx->ray_next_cam, &raygen, sizeof raygen) &&
                      ctx->ray_next_dims[0] == W && ctx->ray_next_dims[1] == H && ctx->ray_next_dims[2] == rows.y0 &&
                      ctx->ray_next_dims[3] == rows.y1 && !ctx->profiling;
