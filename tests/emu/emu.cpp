@@ -239,6 +239,28 @@ extern "C"
         tuv[0] = h.t; tuv[1] = h.u; tuv[2] = h.v;
         return h.prim;
     }
+    // closest hit of a walk seeded the way px_raycast_hinted seeds it: the reference's test on triangle `hint` of `tris`
+    // (any id; out of range = no seed), then bvh.cuh: trace_seeded
+    int emu_closest_hit_seeded(void* gp, const crt_triangle* tris, int n_tris, const float* o, const float* d, int hint, float* tuv)
+    {
+        Hit h;
+        h.prim = -1;
+        h.t = kFltMax;
+        h.u = h.v = 0.0f;
+        if ((uint32_t)hint < (uint32_t)n_tris)
+        {
+            const TriRef tri = tri_at((const float*)tris, hint);
+            float t, u, v;
+            if (ray_triangle(v3(o), v3(d), 0.0f, kFltMax, tri.v(0), tri.v(1), tri.v(2), t, u, v))
+            {
+                h.t = t; h.u = u; h.v = v; h.prim = hint;
+            }
+        }
+        trace_seeded<false>(((EmuGeom*)gp)->view(), v3(o), v3(d), 0.0f, h);
+        if (h.prim < 0) return -1;
+        tuv[0] = h.t; tuv[1] = h.u; tuv[2] = h.v;
+        return h.prim;
+    }
     int emu_any_hit(void* gp, const float* o, const float* d, float tmin, float tmax)
     {
         Hit h;

@@ -236,6 +236,50 @@ def test_hinted_raycast_equals_the_plain_walk_for_any_hint(emu, port):
     emu.geom_free(ge)
 
 
+def test_seeded_walk_on_triangle_soups(emu, port):
+    """bvh.cuh: trace_seeded against the oracle's closest hit on random triangle soups with duplicated, degenerate (zero
+    area, repeated vertex) and coplanar overlapping triangles, random rays (a third of them aimed at a triangle's
+    centroid so that ties on t between duplicates occur), every kind of seed: the true answer, its duplicate with the
+    smaller id, a triangle behind the hit, a random one, out of range — both postponing settings of the host walk"""
+    rng = np.random.default_rng(23)
+    L = emu.lib
+    L.emu_closest_hit_seeded.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    base = small_scene("cornellbox1")
+    for n_tri in (1, 7, 200, 1500):
+        tris = np.zeros(n_tri, base.dtype)
+        c = rng.uniform(-4, 4, (n_tri, 1, 3)).astype(np.float32)
+        tris["vertices"] = c + rng.normal(0, 0.6, (n_tri, 3, 3)).astype(np.float32)
+        k = max(1, n_tri // 10)
+        tris["vertices"][-k:] = tris["vertices"][:k]  # duplicates: the larger id must win
+        if n_tri > 20:
+            tris["vertices"][10] = tris["vertices"][10][[0, 0, 1]]  # repeated vertex
+            tris["vertices"][11] = tris["vertices"][11][0] + np.outer([0.0, 1.0, 2.0], [1.0, 0.5, 0.25]).astype(np.float32)  # collinear
+            tris["vertices"][12] = tris["vertices"][13] * np.float32(0.5) + tris["vertices"][13].mean(0) * np.float32(0.5)  # coplanar, inside 13
+        tris = np.ascontiguousarray(tris)
+        g, ge = port.geom_build(tris), emu.geom_build(tris)
+        n_rays = 600
+        o = rng.uniform(-8, 8, (n_rays, 3)).astype(np.float32)
+        d = rng.normal(0, 1, (n_rays, 3)).astype(np.float32)
+        aim = rng.integers(0, n_tri, n_rays)
+        cen = tris["vertices"][aim].mean(1)
+        d[::3] = (cen - o)[::3]
+        for post in (0, 1):
+            L.emu_set_postpone(post)
+            for i in range(n_rays):
+                want, tuv = port.closest_hit(g, o[i], d[i])
+                seeds = [want, -1, int(rng.integers(0, n_tri)), int(aim[i]), n_tri + 5, -7]
+                if want >= n_tri - k:
+                    seeds.append(want - (n_tri - k))  # the duplicate with the smaller id
+                for hint in seeds:
+                    got_tuv = np.zeros(3, np.float32)
+                    got = L.emu_closest_hit_seeded(ge, tris.ctypes.data, n_tri, o[i].ctypes.data, d[i].ctypes.data, int(hint),
+                                                   got_tuv.ctypes.data)
+                    assert got == want and (want < 0 or same(got_tuv, tuv)), (n_tri, i, hint, got, want)
+        L.emu_set_postpone(0)
+        port.geom_free(g)
+        emu.geom_free(ge)
+
+
 # ---------------------------------------------------------------------------------------------- fused frame
 class EmuFusedFrame:
     """Drives emu_restir_frame_fast (the kernel sequence of crt_restir_di_frame, csrc/kernels_fast.cu) on planar
